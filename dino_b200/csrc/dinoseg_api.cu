@@ -1,0 +1,714 @@
+// libdinoseg.so — C-ABI implementation (see include/dinoseg.h).
+// Host-side orchestration only: weight packing, tensor-map construction, launch sequence.
+// The kernels are in gemm.cuh (tcgen05 GEMM), attention.cuh (tcgen05 flash attention) and
+// kernels.cuh (memory-bound pieces).
+#include "../../include/dinoseg.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace dsg;
+
+namespace {
+
+// -----------------------------------------------------------------------------------------
+// errors
+// -----------------------------------------------------------------------------------------
+thread_local std::string g_create_error;
+
+#define DSG_FAIL(h, ...)                                 \
+  do {                                                   \
+    char _buf[512];                                      \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);           \
+    if (h) (h)->err = _buf; else g_create_error = _buf;  \
+    return -1;                                           \
+  } while (0)
+
+#define DSG_CUDA(h, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) DSG_FAIL(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                                    __FILE__, __LINE__);                                      \
+  } while (0)
+
+// -----------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched through the runtime: no -lcuda needed)
+// -----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// bf16 2-D row-major matrix [rows, cols] (cols contiguous, row pitch ld elements); box {64, box_rows}, SWIZZLE_128B
+bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// qkv [B, N, ld] bf16 viewed as {ld, N, B}; box {64, 128, 1}: rows >= N of a frame read as zeros
+bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint64_t ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {ld, N, B};
+  cuuint64_t strides[2] = {ld * 2, N * ld * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// -----------------------------------------------------------------------------------------
+// kernel launchers
+// -----------------------------------------------------------------------------------------
+constexpr int kGemmBN = 128;
+constexpr int kGemmStages = 3;
+constexpr int kAttnStages = 2;
+
+template <int EPI>
+cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, cudaStream_t s) {
+  auto kern = gemm_bf16_tn_kernel<kGemmBN, EPI, kGemmStages>;
+  constexpr size_t smem = gemm_smem_bytes<kGemmBN, kGemmStages>();
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  dim3 grid((p.N + kGemmBN - 1) / kGemmBN, (p.M + GEMM_BM - 1) / GEMM_BM);
+  kern<<<grid, GEMM_THREADS, smem, s>>>(a, w, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_gemm_t<EPI_BF16>(a, w, p, s);
+    case EPI_GELU_BF16: return launch_gemm_t<EPI_GELU_BF16>(a, w, p, s);
+    case EPI_RESID_F32: return launch_gemm_t<EPI_RESID_F32>(a, w, p, s);
+    case EPI_PATCH_F32: return launch_gemm_t<EPI_PATCH_F32>(a, w, p, s);
+    case EPI_RELU_F32: return launch_gemm_t<EPI_RELU_F32>(a, w, p, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_attention(const CUtensorMap& qkv, const AttnParams& p, cudaStream_t s) {
+  auto kern = attn_fwd_kernel<kAttnStages>;
+  constexpr size_t smem = attn_smem_bytes<kAttnStages>();
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  dim3 grid((p.N + ATT_BM - 1) / ATT_BM, p.H, p.B);
+  kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int M, int D, float eps,
+                             cudaStream_t s) {
+  const int rows_per_block = 8;
+  dim3 grid((M + rows_per_block - 1) / rows_per_block);
+  if (D == 384) layernorm_bf16_kernel<384><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
+  else if (D == 768) layernorm_bf16_kernel<768><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
+  else if (D == 128) layernorm_bf16_kernel<128><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_posembed(const float* pos_src, float* out, int G0, int g, int D, cudaStream_t s) {
+  if (g == G0) {
+    // reference vision_transformer.py:205-206: same grid -> table returned unchanged
+    return cudaMemcpyAsync(out, pos_src, size_t(G0 * G0 + 1) * D * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  }
+  const double sf = (double(g) + 0.1) / double(G0);  // reference :214-217 (python double)
+  const float rscale = float(1.0 / sf);              // ATen compute_scales_value<float>
+  const size_t total = size_t(g * g + 1) * D;
+  posembed_bicubic_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(pos_src, out, G0, g, D, rscale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_im2col(const float* frames, __nv_bfloat16* A, int B, int g, cudaStream_t s) {
+  const size_t total = size_t(B) * 3 * g * 4 * g;
+  im2col_patch8_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(frames, A, B, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_replicate(const uint8_t* lowres, int64_t* labels, int B, int g, int p, cudaStream_t s) {
+  const int W = g * p;
+  const size_t total = (W & 1) ? size_t(B) * W * W : size_t(B) * W * (W / 2);
+  if (total == 0) return cudaSuccess;
+  replicate_labels_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(lowres, reinterpret_cast<long long*>(labels),
+                                                                        B, g, p);
+  return cudaGetLastError();
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct BlockW {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  __nv_bfloat16 *qkv_w = nullptr, *proj_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
+  float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+};
+
+struct WeightSlot {
+  int kind;  // 0 = fp32 copy, 1 = bf16 convert, 2 = head layer_2 (fp32 copy + transposed/padded copy)
+  void* dst;
+  std::vector<int64_t> shape;
+};
+
+}  // namespace
+
+struct dinoseg {
+  dinoseg_cfg cfg{};
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+
+  // parameters
+  float* cls = nullptr;
+  float* pos_src = nullptr;
+  __nv_bfloat16* pe_w = nullptr;
+  float* pe_b = nullptr;
+  CUtensorMap tm_pe;
+  std::vector<BlockW> blocks;
+  float *norm_g = nullptr, *norm_b = nullptr;
+  __nv_bfloat16* h1_w = nullptr;
+  float* h1_b = nullptr;
+  CUtensorMap tm_h1;
+  float *w2 = nullptr, *w2t = nullptr, *b2 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  std::map<std::string, WeightSlot> slots;
+  std::set<std::string> have;
+  std::vector<void*> allocs;
+
+  // resolution state
+  int res = 0, g = 0, P = 0, Ntok = 0, p_rep = 0;
+  float* pos = nullptr;
+  size_t pos_cap = 0;
+
+  // workspace carve-up (valid for ws_ptr / ws_batch / ws_res)
+  void* ws_ptr = nullptr;
+  int ws_batch = 0, ws_res = 0;
+  float* x = nullptr;
+  __nv_bfloat16* abuf = nullptr;
+  __nv_bfloat16* qkv = nullptr;
+  __nv_bfloat16* hid = nullptr;
+  uint8_t* lowres_ws = nullptr;
+  CUtensorMap tm_im2col, tm_abuf, tm_hid, tm_qkv3d;
+
+  int debug_stop = 0;
+  int launches = 0;
+
+  // predict_host staging (grow-only)
+  float* st_frames = nullptr;
+  size_t st_frames_cap = 0;
+  void* st_ws = nullptr;
+  size_t st_ws_cap = 0;
+  uint8_t* st_lowres = nullptr;
+  size_t st_lowres_cap = 0;
+  int64_t* st_labels = nullptr;
+  size_t st_labels_cap = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(dinoseg* h, T** p, size_t count) {
+  void* q = nullptr;
+  DSG_CUDA(h, cudaMalloc(&q, count * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+int add_slot(dinoseg* h, const std::string& key, int kind, void* dst, std::vector<int64_t> shape) {
+  h->slots[key] = WeightSlot{kind, dst, std::move(shape)};
+  return 0;
+}
+
+struct WsLayout {
+  size_t x, abuf, qkv, hid, lowres, total;
+};
+
+WsLayout ws_layout(const dinoseg* h, int batch) {
+  const size_t M = size_t(batch) * h->Ntok;
+  const size_t D = h->cfg.embed_dim;
+  WsLayout L{};
+  size_t off = 0;
+  L.x = off; off = align_up(off + M * D * 4, 1024);
+  L.abuf = off; off = align_up(off + M * D * 2, 1024);
+  L.qkv = off; off = align_up(off + M * 3 * D * 2, 1024);
+  size_t hid_bytes = M * size_t(h->cfg.mlp_hidden) * 2;
+  const size_t h1_bytes = M * size_t(h->cfg.head_h1) * 4;
+  const size_t im2col_bytes = size_t(batch) * h->P * 192 * 2;
+  if (h1_bytes > hid_bytes) hid_bytes = h1_bytes;
+  if (im2col_bytes > hid_bytes) hid_bytes = im2col_bytes;
+  L.hid = off; off = align_up(off + hid_bytes, 1024);
+  L.lowres = off; off = align_up(off + size_t(batch) * h->P, 1024);
+  L.total = off;
+  return L;
+}
+
+int bind_workspace(dinoseg* h, void* ws, size_t ws_bytes, int batch) {
+  const WsLayout L = ws_layout(h, batch);
+  if (ws_bytes < L.total) DSG_FAIL(h, "workspace too small: %zu < %zu bytes", ws_bytes, L.total);
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) DSG_FAIL(h, "workspace must be 1024-byte aligned");
+  if (h->ws_ptr == ws && h->ws_batch == batch && h->ws_res == h->res) return 0;
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  h->x = reinterpret_cast<float*>(base + L.x);
+  h->abuf = reinterpret_cast<__nv_bfloat16*>(base + L.abuf);
+  h->qkv = reinterpret_cast<__nv_bfloat16*>(base + L.qkv);
+  h->hid = reinterpret_cast<__nv_bfloat16*>(base + L.hid);
+  h->lowres_ws = base + L.lowres;
+  const uint64_t M = uint64_t(batch) * h->Ntok;
+  const uint64_t D = h->cfg.embed_dim;
+  bool ok = true;
+  ok &= make_tmap_2d(&h->tm_im2col, h->hid, uint64_t(batch) * h->P, 192, 192, GEMM_BM);
+  ok &= make_tmap_2d(&h->tm_abuf, h->abuf, M, D, D, GEMM_BM);
+  ok &= make_tmap_2d(&h->tm_hid, h->hid, M, h->cfg.mlp_hidden, h->cfg.mlp_hidden, GEMM_BM);
+  ok &= make_tmap_qkv(&h->tm_qkv3d, h->qkv, batch, h->Ntok, 3 * D);
+  if (!ok) DSG_FAIL(h, "cuTensorMapEncodeTiled failed for the workspace tensor maps");
+  h->ws_ptr = ws;
+  h->ws_batch = batch;
+  h->ws_res = h->res;
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* dinoseg_last_error(const dinoseg_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
+  dinoseg* null_h = nullptr;
+  if (!cfg || !out) DSG_FAIL(null_h, "dinoseg_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    DSG_FAIL(null_h, "dinoseg_create: no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) DSG_FAIL(null_h, "dinoseg_create: invalid device %d", device);
+  cudaDeviceProp prop;
+  DSG_CUDA(null_h, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    DSG_FAIL(null_h, "dinoseg_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+             prop.major, prop.minor);
+  if (cfg->embed_dim != 384 && cfg->embed_dim != 768) DSG_FAIL(null_h, "embed_dim must be 384 or 768");
+  if (cfg->num_heads * 64 != cfg->embed_dim) DSG_FAIL(null_h, "head_dim must be 64 (num_heads = embed_dim/64)");
+  if (cfg->patch != 8) DSG_FAIL(null_h, "patch size must be 8");
+  if (cfg->n_blocks < 0 || cfg->n_blocks > 12) DSG_FAIL(null_h, "n_blocks out of range");
+  if (cfg->n_classes < 1 || cfg->n_classes > HEAD_MAX_C) DSG_FAIL(null_h, "n_classes must be in [1,%d]", HEAD_MAX_C);
+  if (cfg->head_kind != 0) DSG_FAIL(null_h, "only the 'mlp' head (head_kind=0) is implemented");
+  if (cfg->head_h1 % 8 != 0 || cfg->head_h1 < 104 || cfg->head_h1 > 256 || cfg->head_h2 > 104 || cfg->head_h2 < 1)
+    DSG_FAIL(null_h, "unsupported head widths %d/%d", cfg->head_h1, cfg->head_h2);
+  if (cfg->mlp_hidden % 64 != 0) DSG_FAIL(null_h, "mlp_hidden must be a multiple of 64");
+  if (!get_encode()) DSG_FAIL(null_h, "cuTensorMapEncodeTiled not available from the driver");
+  DSG_CUDA(null_h, cudaSetDevice(device));
+
+  dinoseg* h = new dinoseg();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  const int D = cfg->embed_dim, HID = cfg->mlp_hidden, G0 = cfg->pos_grid, C = cfg->n_classes;
+  const int H1 = cfg->head_h1, H2 = cfg->head_h2;
+  int rc = 0;
+  rc |= dev_alloc(h, &h->cls, D);
+  rc |= dev_alloc(h, &h->pos_src, size_t(G0 * G0 + 1) * D);
+  rc |= dev_alloc(h, &h->pe_w, size_t(D) * 192);
+  rc |= dev_alloc(h, &h->pe_b, D);
+  rc |= dev_alloc(h, &h->norm_g, D);
+  rc |= dev_alloc(h, &h->norm_b, D);
+  rc |= dev_alloc(h, &h->h1_w, size_t(H1) * D);
+  rc |= dev_alloc(h, &h->h1_b, H1);
+  rc |= dev_alloc(h, &h->w2, size_t(H2) * H1);
+  rc |= dev_alloc(h, &h->w2t, size_t(H1) * HT_H2P);
+  rc |= dev_alloc(h, &h->b2, H2);
+  rc |= dev_alloc(h, &h->w3, size_t(C) * H2);
+  rc |= dev_alloc(h, &h->b3, C);
+  add_slot(h, "dino.cls_token", 0, h->cls, {1, 1, D});
+  add_slot(h, "dino.pos_embed", 0, h->pos_src, {1, G0 * G0 + 1, D});
+  add_slot(h, "dino.patch_embed.proj.weight", 1, h->pe_w, {D, 3, 8, 8});
+  add_slot(h, "dino.patch_embed.proj.bias", 0, h->pe_b, {D});
+  add_slot(h, "dino.norm.weight", 0, h->norm_g, {D});
+  add_slot(h, "dino.norm.bias", 0, h->norm_b, {D});
+  add_slot(h, "clf.layer_1.weight", 1, h->h1_w, {H1, D});
+  add_slot(h, "clf.layer_1.bias", 0, h->h1_b, {H1});
+  add_slot(h, "clf.layer_2.weight", 2, h->w2, {H2, H1});
+  add_slot(h, "clf.layer_2.bias", 0, h->b2, {H2});
+  add_slot(h, "clf.layer_3.weight", 0, h->w3, {C, H2});
+  add_slot(h, "clf.layer_3.bias", 0, h->b3, {C});
+  h->blocks.resize(cfg->n_blocks);
+  for (int i = 0; i < cfg->n_blocks && rc == 0; ++i) {
+    BlockW& b = h->blocks[i];
+    const std::string pre = "dino.blocks." + std::to_string(i) + ".";
+    rc |= dev_alloc(h, &b.ln1_g, D); rc |= dev_alloc(h, &b.ln1_b, D);
+    rc |= dev_alloc(h, &b.ln2_g, D); rc |= dev_alloc(h, &b.ln2_b, D);
+    rc |= dev_alloc(h, &b.qkv_w, size_t(3) * D * D); rc |= dev_alloc(h, &b.qkv_b, 3 * D);
+    rc |= dev_alloc(h, &b.proj_w, size_t(D) * D); rc |= dev_alloc(h, &b.proj_b, D);
+    rc |= dev_alloc(h, &b.fc1_w, size_t(HID) * D); rc |= dev_alloc(h, &b.fc1_b, HID);
+    rc |= dev_alloc(h, &b.fc2_w, size_t(D) * HID); rc |= dev_alloc(h, &b.fc2_b, D);
+    if (rc) break;
+    add_slot(h, pre + "norm1.weight", 0, b.ln1_g, {D}); add_slot(h, pre + "norm1.bias", 0, b.ln1_b, {D});
+    add_slot(h, pre + "norm2.weight", 0, b.ln2_g, {D}); add_slot(h, pre + "norm2.bias", 0, b.ln2_b, {D});
+    add_slot(h, pre + "attn.qkv.weight", 1, b.qkv_w, {3 * D, D}); add_slot(h, pre + "attn.qkv.bias", 0, b.qkv_b, {3 * D});
+    add_slot(h, pre + "attn.proj.weight", 1, b.proj_w, {D, D}); add_slot(h, pre + "attn.proj.bias", 0, b.proj_b, {D});
+    add_slot(h, pre + "mlp.fc1.weight", 1, b.fc1_w, {HID, D}); add_slot(h, pre + "mlp.fc1.bias", 0, b.fc1_b, {HID});
+    add_slot(h, pre + "mlp.fc2.weight", 1, b.fc2_w, {D, HID}); add_slot(h, pre + "mlp.fc2.bias", 0, b.fc2_b, {D});
+    bool ok = true;
+    ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, kGemmBN);
+    ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, kGemmBN);
+    ok &= make_tmap_2d(&b.tm_fc1, b.fc1_w, HID, D, D, kGemmBN);
+    ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, kGemmBN);
+    if (!ok) { h->err = "cuTensorMapEncodeTiled failed for block weights"; rc = -1; }
+  }
+  if (rc == 0) {
+    bool ok = make_tmap_2d(&h->tm_pe, h->pe_w, D, 192, 192, kGemmBN);
+    ok &= make_tmap_2d(&h->tm_h1, h->h1_w, H1, D, D, kGemmBN);
+    if (!ok) { h->err = "cuTensorMapEncodeTiled failed for patch/head weights"; rc = -1; }
+  }
+  if (rc != 0) {
+    g_create_error = h->err;
+    dinoseg_destroy(h);
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+void dinoseg_destroy(dinoseg_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->pos) cudaFree(h->pos);
+  if (h->st_frames) cudaFree(h->st_frames);
+  if (h->st_ws) cudaFree(h->st_ws);
+  if (h->st_lowres) cudaFree(h->st_lowres);
+  if (h->st_labels) cudaFree(h->st_labels);
+  delete h;
+}
+
+int dinoseg_set_weight(dinoseg_t* h, const char* key, const float* dev_ptr, const int64_t* shape, int ndim,
+                       void* stream) {
+  if (!h) return -1;
+  if (!key || !dev_ptr || !shape) DSG_FAIL(h, "dinoseg_set_weight: null argument");
+  auto it = h->slots.find(key);
+  if (it == h->slots.end()) DSG_FAIL(h, "dinoseg_set_weight: unexpected key '%s'", key);
+  const WeightSlot& sl = it->second;
+  bool same = int(sl.shape.size()) == ndim;
+  size_t n = 1;
+  for (int i = 0; same && i < ndim; ++i) same = sl.shape[i] == shape[i];
+  for (int64_t d : sl.shape) n *= size_t(d);
+  if (!same) {
+    std::string want, got;
+    for (int64_t d : sl.shape) want += std::to_string(d) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    DSG_FAIL(h, "dinoseg_set_weight: size mismatch for %s: expected (%s) got (%s)", key, want.c_str(), got.c_str());
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  if (sl.kind == 1) {
+    const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, 4096));
+    f32_to_bf16_kernel<<<blocks, 256, 0, s>>>(dev_ptr, static_cast<__nv_bfloat16*>(sl.dst), n);
+    DSG_CUDA(h, cudaGetLastError());
+  } else {
+    DSG_CUDA(h, cudaMemcpyAsync(sl.dst, dev_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (sl.kind == 2) {
+      const int H2 = h->cfg.head_h2, H1 = h->cfg.head_h1;
+      transpose_pad_kernel<<<(H1 * HT_H2P + 255) / 256, 256, 0, s>>>(h->w2, h->w2t, H2, H1, HT_H2P);
+      DSG_CUDA(h, cudaGetLastError());
+    }
+  }
+  h->have.insert(key);
+  return 0;
+}
+
+int dinoseg_missing_weights(const dinoseg_t* h) {
+  if (!h) return -1;
+  return int(h->slots.size()) - int(h->have.size());
+}
+
+int dinoseg_set_resolution(dinoseg_t* h, int resolution, void* stream) {
+  if (!h) return -1;
+  if (resolution <= 0 || resolution % 8 != 0) DSG_FAIL(h, "Resolution should be a multiple of 8.");
+  if (!h->have.count("dino.pos_embed")) DSG_FAIL(h, "dinoseg_set_resolution: dino.pos_embed has not been set");
+  const int g = resolution / 8;
+  if (g > 480) DSG_FAIL(h, "resolution %d too large (patch grid %d > 480)", resolution, g);
+  const int D = h->cfg.embed_dim;
+  const size_t need = size_t(g * g + 1) * D;
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (need > h->pos_cap) {
+    if (h->pos) {
+      DSG_CUDA(h, cudaStreamSynchronize(s));
+      DSG_CUDA(h, cudaFree(h->pos));
+      h->pos = nullptr;
+    }
+    DSG_CUDA(h, cudaMalloc(&h->pos, need * sizeof(float)));
+    h->pos_cap = need;
+  }
+  DSG_CUDA(h, launch_posembed(h->pos_src, h->pos, h->cfg.pos_grid, g, D, s));
+  h->res = resolution;
+  h->g = g;
+  h->P = g * g;
+  h->Ntok = g * g + 1;
+  h->p_rep = 480 / g;  // reference pl_torch_modules.py:297
+  h->ws_ptr = nullptr;  // tensor maps depend on Ntok
+  return 0;
+}
+
+size_t dinoseg_workspace_bytes(const dinoseg_t* h, int batch) {
+  if (!h || h->res == 0 || batch <= 0) return 0;
+  return ws_layout(h, batch).total;
+}
+
+int dinoseg_set_debug_stop(dinoseg_t* h, int stage) {
+  if (!h) return -1;
+  h->debug_stop = stage;
+  return 0;
+}
+
+int dinoseg_last_launch_count(const dinoseg_t* h) { return h ? h->launches : -1; }
+
+int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprobs, uint8_t* lowres, int64_t* labels,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return -1;
+  if (h->res == 0) DSG_FAIL(h, "dinoseg_forward: call dinoseg_set_resolution first");
+  if (dinoseg_missing_weights(h) != 0) {
+    std::string miss;
+    for (auto& kv : h->slots)
+      if (!h->have.count(kv.first)) { miss = kv.first; break; }
+    DSG_FAIL(h, "dinoseg_forward: %d parameters not set (first missing: %s)", dinoseg_missing_weights(h),
+             miss.c_str());
+  }
+  if (!frames || batch <= 0 || !workspace) DSG_FAIL(h, "dinoseg_forward: bad arguments");
+  if (size_t(batch) * h->Ntok > size_t(INT32_MAX) / 4) DSG_FAIL(h, "dinoseg_forward: batch too large");
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  if (bind_workspace(h, workspace, workspace_bytes, batch) != 0) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int D = h->cfg.embed_dim, HID = h->cfg.mlp_hidden, H = h->cfg.num_heads;
+  const int M = batch * h->Ntok;
+  const float eps = h->cfg.ln_eps;
+  int n = 0;
+  h->launches = 0;
+  const int stop = h->debug_stop;
+
+  // ---- prepare_tokens (vision_transformer.py:224-235) ----
+  DSG_CUDA(h, launch_im2col(frames, h->hid, batch, h->g, s)); ++n;
+  cls_row_kernel<<<(batch * D + 255) / 256, 256, 0, s>>>(h->cls, h->pos, h->x, batch, h->Ntok, D);
+  DSG_CUDA(h, cudaGetLastError()); ++n;
+  {
+    GemmParams p{};
+    p.M = batch * h->P; p.N = D; p.K = 192; p.bias = h->pe_b; p.out = h->x; p.ldo = D;
+    p.pos = h->pos; p.P = h->P; p.Ntok = h->Ntok;
+    DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, h->tm_im2col, h->tm_pe, p, s)); ++n;
+  }
+  if (stop == 1) { h->launches = n; return 0; }
+
+  // ---- transformer blocks (vision_transformer.py:122-140) ----
+  for (int i = 0; i < h->cfg.n_blocks; ++i) {
+    BlockW& b = h->blocks[i];
+    DSG_CUDA(h, launch_layernorm(h->x, b.ln1_g, b.ln1_b, h->abuf, M, D, eps, s)); ++n;
+    {
+      GemmParams p{};
+      p.M = M; p.N = 3 * D; p.K = D; p.bias = b.qkv_b; p.out = h->qkv; p.ldo = 3 * D;
+      p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
+      DSG_CUDA(h, launch_gemm(EPI_BF16, h->tm_abuf, b.tm_qkv, p, s)); ++n;
+    }
+    if (stop == 2 + 3 * i) { h->launches = n; return 0; }
+    {
+      AttnParams p{};
+      p.B = batch; p.H = H; p.N = h->Ntok; p.D = D; p.out = h->abuf;
+      DSG_CUDA(h, launch_attention(h->tm_qkv3d, p, s)); ++n;
+    }
+    {
+      GemmParams p{};
+      p.M = M; p.N = D; p.K = D; p.bias = b.proj_b; p.out = h->x; p.ldo = D;
+      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_abuf, b.tm_proj, p, s)); ++n;
+    }
+    if (stop == 3 + 3 * i) { h->launches = n; return 0; }
+    DSG_CUDA(h, launch_layernorm(h->x, b.ln2_g, b.ln2_b, h->abuf, M, D, eps, s)); ++n;
+    {
+      GemmParams p{};
+      p.M = M; p.N = HID; p.K = D; p.bias = b.fc1_b; p.out = h->hid; p.ldo = HID;
+      DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, h->tm_abuf, b.tm_fc1, p, s)); ++n;
+    }
+    {
+      GemmParams p{};
+      p.M = M; p.N = D; p.K = HID; p.bias = b.fc2_b; p.out = h->x; p.ldo = D;
+      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_hid, b.tm_fc2, p, s)); ++n;
+    }
+    if (stop == 4 + 3 * i) { h->launches = n; return 0; }
+  }
+
+  // ---- final norm + head (vision_transformer.py:243, pl_torch_modules.py:243-255) ----
+  DSG_CUDA(h, launch_layernorm(h->x, h->norm_g, h->norm_b, h->abuf, M, D, eps, s)); ++n;
+  float* h1 = reinterpret_cast<float*>(h->hid);
+  {
+    GemmParams p{};
+    p.M = M; p.N = h->cfg.head_h1; p.K = D; p.bias = h->h1_b; p.out = h1; p.ldo = h->cfg.head_h1;
+    DSG_CUDA(h, launch_gemm(EPI_RELU_F32, h->tm_abuf, h->tm_h1, p, s)); ++n;
+  }
+  uint8_t* lr = lowres ? lowres : h->lowres_ws;
+  {
+    const size_t smem = head_tail_smem_bytes(h->cfg.head_h1);
+    static bool attr[64] = {};
+    if (!attr[h->device & 63]) {
+      DSG_CUDA(h, cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      attr[h->device & 63] = true;
+    }
+    const int ntiles = (batch * h->P + HT_ROWS - 1) / HT_ROWS;
+    const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
+    head_tail_kernel<<<grid, 256, smem, s>>>(h1, h->w2t, h->b2, h->w3, h->b3, logprobs, lr, batch, h->P, h->Ntok,
+                                             h->cfg.head_h1, h->cfg.head_h2, h->cfg.n_classes);
+    DSG_CUDA(h, cudaGetLastError()); ++n;
+  }
+  if (labels) { DSG_CUDA(h, launch_replicate(lr, labels, batch, h->g, h->p_rep, s)); ++n; }
+  h->launches = n;
+  return 0;
+}
+
+int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
+                         int64_t* host_labels, void* stream) {
+  if (!h) return -1;
+  if (h->res == 0) DSG_FAIL(h, "dinoseg_predict_host: call dinoseg_set_resolution first");
+  if (!host_frames || batch <= 0) DSG_FAIL(h, "dinoseg_predict_host: bad arguments");
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t fbytes = size_t(batch) * 3 * h->res * h->res * sizeof(float);
+  const size_t wbytes = dinoseg_workspace_bytes(h, batch);
+  const size_t lbytes = size_t(batch) * h->P;
+  const size_t W = size_t(h->g) * h->p_rep;
+  const size_t obytes = size_t(batch) * W * W * sizeof(int64_t);
+  auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) { cudaStreamSynchronize(s); cudaFree(*p); *p = nullptr; *cap = 0; }
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  DSG_CUDA(h, grow(reinterpret_cast<void**>(&h->st_frames), &h->st_frames_cap, fbytes));
+  DSG_CUDA(h, grow(&h->st_ws, &h->st_ws_cap, wbytes));
+  DSG_CUDA(h, grow(reinterpret_cast<void**>(&h->st_lowres), &h->st_lowres_cap, lbytes));
+  if (host_labels && obytes) DSG_CUDA(h, grow(reinterpret_cast<void**>(&h->st_labels), &h->st_labels_cap, obytes));
+  DSG_CUDA(h, cudaMemcpyAsync(h->st_frames, host_frames, fbytes, cudaMemcpyHostToDevice, s));
+  if (dinoseg_forward(h, h->st_frames, batch, nullptr, h->st_lowres, host_labels ? h->st_labels : nullptr, h->st_ws,
+                      h->st_ws_cap, s) != 0)
+    return -1;
+  if (host_lowres) DSG_CUDA(h, cudaMemcpyAsync(host_lowres, h->st_lowres, lbytes, cudaMemcpyDeviceToHost, s));
+  if (host_labels && obytes) DSG_CUDA(h, cudaMemcpyAsync(host_labels, h->st_labels, obytes, cudaMemcpyDeviceToHost, s));
+  DSG_CUDA(h, cudaStreamSynchronize(s));
+  return 0;
+}
+
+int dinoseg_argmax_replicate(const float* logprobs, int batch, int g, int n_classes, int p, uint8_t* lowres,
+                             int64_t* labels, void* stream) {
+  if (!logprobs || !lowres || batch <= 0 || g <= 0 || n_classes < 1 || n_classes > HEAD_MAX_C || p < 0) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows = batch * g * g;
+  argmax_rows_kernel<<<(rows + 255) / 256, 256, 0, s>>>(logprobs, lowres, rows, n_classes);
+  if (cudaGetLastError() != cudaSuccess) return -2;
+  if (labels && p > 0 && launch_replicate(lowres, labels, batch, g, p, s) != cudaSuccess) return -3;
+  return 0;
+}
+
+int64_t dinoseg_copy_buffer(dinoseg_t* h, const char* name, void* dst, size_t dst_bytes, void* stream) {
+  if (!h || !name || !dst) return -1;
+  const void* src = nullptr;
+  size_t bytes = 0;
+  const size_t M = size_t(h->ws_batch) * h->Ntok, D = h->cfg.embed_dim;
+  const std::string nm(name);
+  if (nm == "pos") { src = h->pos; bytes = size_t(h->Ntok) * D * 4; }
+  else if (nm == "x") { src = h->x; bytes = M * D * 4; }
+  else if (nm == "abuf") { src = h->abuf; bytes = M * D * 2; }
+  else if (nm == "qkv") { src = h->qkv; bytes = M * 3 * D * 2; }
+  else DSG_FAIL(h, "dinoseg_copy_buffer: unknown buffer '%s'", name);
+  if (!src || bytes == 0) DSG_FAIL(h, "dinoseg_copy_buffer: buffer '%s' not available yet", name);
+  if (bytes > dst_bytes) DSG_FAIL(h, "dinoseg_copy_buffer: destination too small (%zu < %zu)", dst_bytes, bytes);
+  DSG_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return int64_t(bytes);
+}
+
+// ---- kernel-level entry points ------------------------------------------------------------
+int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo, int epi,
+                    float col_scale, int scale_cols, const float* pos, int P, int Ntok, void* stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0) return -1;
+  if ((epi == EPI_BF16 || epi == EPI_GELU_BF16) ? (N % 8 != 0) : (N % 4 != 0)) return -1;
+  CUtensorMap ta, tw;
+  if (!make_tmap_2d(&ta, A, M, K, K, GEMM_BM) || !make_tmap_2d(&tw, W, N, K, K, kGemmBN)) return -2;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = ldo;
+  p.col_scale = col_scale; p.scale_cols = scale_cols; p.pos = pos; p.P = P; p.Ntok = Ntok;
+  return launch_gemm(epi, ta, tw, p, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {
+  if (!qkv || !out || B <= 0 || N <= 0 || H <= 0) return -1;
+  CUtensorMap tq;
+  if (!make_tmap_qkv(&tq, qkv, B, N, uint64_t(3) * H * 64)) return -2;
+  AttnParams p{};
+  p.B = B; p.H = H; p.N = N; p.D = H * 64; p.out = static_cast<__nv_bfloat16*>(out);
+  return launch_attention(tq, p, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,
+                         void* stream) {
+  return launch_layernorm(x, gamma, beta, static_cast<__nv_bfloat16*>(y), M, D, eps,
+                          static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+int dinoseg_op_posembed(const float* pos_src, float* out, int G0, int g, int D, void* stream) {
+  return launch_posembed(pos_src, out, G0, g, D, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+int dinoseg_op_im2col(const float* frames, void* A, int B, int g, void* stream) {
+  return launch_im2col(frames, static_cast<__nv_bfloat16*>(A), B, g, static_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? 0 : -1;
+}
+
+int dinoseg_op_f32_to_bf16(const float* in, void* out, size_t n, void* stream) {
+  const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, 4096));
+  f32_to_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // extern "C"

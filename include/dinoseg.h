@@ -1,0 +1,116 @@
+/* dinoseg.h — C ABI of libdinoseg.so: the B200 (sm_100a) implementation of the DINOSeg
+ * inference hot path of sachaMorin/dino.
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python method surface of
+ * `DINOSeg` (dt_segmentation/src/pl_torch_modules.py).  Each entry point below names the
+ * reference interface it replaces; `dino_b200/model.py` is the Python host that binds them
+ * with ctypes and re-creates that method surface.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *    default stream); every call is asynchronous on that stream unless stated otherwise.
+ *  - return value 0 = ok, negative = error; dinoseg_last_error(h) gives the message
+ *    (stored per handle; for a failed dinoseg_create use dinoseg_last_error(NULL)).
+ *  - one handle per (GPU, stream); a handle is not thread-safe, independent handles are.
+ *  - there is NO CPU path: dinoseg_create fails unless the device is compute capability 10.x.
+ */
+#ifndef DINOSEG_H_
+#define DINOSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dinoseg dinoseg_t;
+
+/* Architecture of the truncated ViT + head.
+ * Replaces: DINOSeg.__init__ vit branch (pl_torch_modules.py:173-183, heads :219-222) and
+ * vit_small / vit_base (vision_transformer.py:300-311). */
+typedef struct dinoseg_cfg {
+  int32_t embed_dim;  /* 384 (ViT-S) or 768 (ViT-B); multiple of 128 */
+  int32_t num_heads;  /* embed_dim / 64 */
+  int32_t mlp_hidden; /* 4 * embed_dim */
+  int32_t n_blocks;   /* number of leading transformer blocks kept (pl_torch_modules.py:177) */
+  int32_t patch;      /* 8 */
+  int32_t pos_grid;   /* side of the stored positional grid: 28 (img 224 / patch 8) */
+  int32_t n_classes;  /* <= 16 */
+  int32_t head_h1;    /* 200 (MLP head, pl_torch_modules.py:113) */
+  int32_t head_h2;    /* 100 (pl_torch_modules.py:114) */
+  int32_t head_kind;  /* 0 = 'mlp' head (pl_torch_modules.py:108-124) */
+  float ln_eps;       /* 1e-6 (vision_transformer.py:303) */
+} dinoseg_cfg;
+
+/* Replaces DINOSeg.__init__ (pl_torch_modules.py:144-237) for the vit backbone. */
+int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out);
+void dinoseg_destroy(dinoseg_t* h);
+const char* dinoseg_last_error(const dinoseg_t* h);
+
+/* Copy one fp32 parameter (device pointer) into the handle, keyed by its reference
+ * state_dict name ("dino.blocks.0.attn.qkv.weight", "clf.layer_1.bias", ...).
+ * Replaces: load_state_dict inside LightningModule.load_from_checkpoint (README.md:31). */
+int dinoseg_set_weight(dinoseg_t* h, const char* key, const float* dev_ptr, const int64_t* shape, int ndim,
+                       void* stream);
+/* number of parameters still missing (0 = ready) */
+int dinoseg_missing_weights(const dinoseg_t* h);
+
+/* Replaces DINOSeg.set_resolution (pl_torch_modules.py:270-274); also builds the cached
+ * bicubic positional table (vision_transformer.py:202-222).  resolution % 8 != 0 -> error
+ * "Resolution should be a multiple of 8." */
+int dinoseg_set_resolution(dinoseg_t* h, int resolution, void* stream);
+
+size_t dinoseg_workspace_bytes(const dinoseg_t* h, int batch);
+
+/* Replaces DINOSeg.forward (pl_torch_modules.py:239-256) + the argmax / np.kron tail of
+ * DINOSeg.predict (:294-298), batched.
+ *   frames   : device, fp32 [batch,3,r,r] NCHW, already normalised
+ *   logprobs : device, fp32 [batch*P, C] or NULL        (forward's return value)
+ *   lowres   : device, uint8 [batch, g, g] or NULL       (argmax per patch)
+ *   labels   : device, int64 [batch, g*p, g*p] or NULL   (p = 480 / g; predict's return value)
+ *   workspace: device scratch of at least dinoseg_workspace_bytes(h, batch) bytes, 1024-aligned */
+int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprobs, uint8_t* lowres,
+                    int64_t* labels, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same computation with HOST buffers (pinned memory recommended): copies the frames to the
+ * device, runs dinoseg_forward, copies the label maps back and SYNCHRONISES the stream.
+ * This is the call that replaces a loop of DINOSeg.predict() (pl_torch_modules.py:276-300)
+ * after preprocessing.  host_lowres / host_labels may be NULL individually. */
+int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
+                         int64_t* host_labels, void* stream);
+
+/* Output side of predict() on given log-probs: argmax (first max wins, NaN counts as max)
+ * then p x p block replication.  Bit-exact w.r.t. torch.argmax + np.kron.
+ * (pl_torch_modules.py:295-298).  rows = batch*g*g. */
+int dinoseg_argmax_replicate(const float* logprobs, int batch, int g, int n_classes, int p, uint8_t* lowres,
+                             int64_t* labels, void* stream);
+
+/* ---- introspection (used by tests and bench) ------------------------------------------ */
+/* Copy an internal device buffer of the LAST forward into dst (device pointer).
+ * names: "pos" fp32 [N,D] | "x" fp32 [B*N,D] residual stream after the last executed stage |
+ * "abuf" bf16 [B*N,D] | "qkv" bf16 [B*N,3D].  Returns the number of bytes copied or <0. */
+int64_t dinoseg_copy_buffer(dinoseg_t* h, const char* name, void* dst, size_t dst_bytes, void* stream);
+/* Stop the next forwards after stage k (debug): 0 = run everything, 1 = after prepare_tokens,
+ * 2+3*i = after block i's qkv GEMM, 3+3*i = after block i's attention+proj, 4+3*i = after block i */
+int dinoseg_set_debug_stop(dinoseg_t* h, int stage);
+/* number of kernels launched by the last dinoseg_forward */
+int dinoseg_last_launch_count(const dinoseg_t* h);
+
+/* ---- kernel-level entry points (parity tests of the individual CUDA kernels) ----------- */
+/* C[M,N] = A[M,K] bf16 x W[N,K]^T bf16 with epilogue `epi` (see csrc/gemm.cuh EPI_*) */
+int dinoseg_op_gemm(const void* A_bf16, const void* W_bf16, const float* bias, void* out, int M, int N, int K,
+                    int ldo, int epi, float col_scale, int scale_cols, const float* pos, int P, int Ntok,
+                    void* stream);
+/* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16 (q pre-scaled) */
+int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int H, void* stream);
+int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
+                         float eps, void* stream);
+int dinoseg_op_posembed(const float* pos_src, float* out, int G0, int g, int D, void* stream);
+int dinoseg_op_im2col(const float* frames, void* A_bf16, int B, int g, void* stream);
+int dinoseg_op_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOSEG_H_ */
