@@ -236,6 +236,12 @@ struct dinoseg {
   int debug_stop = 0;
   int launches = 0;
 
+  // optional per-kernel-kind timing (cudaEvents around every launch of a forward)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;       // 2 per launch slot
+  std::vector<int> ev_kind;          // kind of each recorded launch
+  int ev_used = 0;
+
   // predict_host staging (grow-only)
   float* st_frames = nullptr;
   size_t st_frames_cap = 0;
@@ -311,6 +317,29 @@ int bind_workspace(dinoseg* h, void* ws, size_t ws_bytes, int batch) {
   return 0;
 }
 
+}  // namespace
+
+namespace {
+enum Kind { K_IM2COL = 0, K_CLS, K_GEMM_PATCH, K_LN, K_GEMM_QKV, K_ATTN, K_GEMM_PROJ, K_GEMM_FC1, K_GEMM_FC2,
+            K_GEMM_HEAD, K_HEAD_TAIL, K_REPLICATE, K_COUNT };
+const char* const kKindNames[K_COUNT] = {"im2col", "cls_row", "gemm_patch", "layernorm", "gemm_qkv", "attention",
+                                         "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_head", "head_tail", "replicate"};
+
+// RAII pair of events around one launch (no-op unless profiling is on)
+struct LaunchScope {
+  dinoseg* h; cudaStream_t s; int slot;
+  LaunchScope(dinoseg* h_, int kind, cudaStream_t s_) : h(h_), s(s_), slot(-1) {
+    if (!h->profile) return;
+    slot = h->ev_used++;
+    while (int(h->ev.size()) < 2 * (slot + 1)) {
+      cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e);
+    }
+    if (int(h->ev_kind.size()) <= slot) h->ev_kind.resize(slot + 1);
+    h->ev_kind[slot] = kind;
+    cudaEventRecord(h->ev[2 * slot], s);
+  }
+  ~LaunchScope() { if (slot >= 0) cudaEventRecord(h->ev[2 * slot + 1], s); }
+};
 }  // namespace
 
 // =========================================================================================
@@ -424,6 +453,7 @@ void dinoseg_destroy(dinoseg_t* h) {
   if (h->st_ws) cudaFree(h->st_ws);
   if (h->st_lowres) cudaFree(h->st_lowres);
   if (h->st_labels) cudaFree(h->st_labels);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -509,6 +539,31 @@ int dinoseg_set_debug_stop(dinoseg_t* h, int stage) {
 
 int dinoseg_last_launch_count(const dinoseg_t* h) { return h ? h->launches : -1; }
 
+int dinoseg_profile_enable(dinoseg_t* h, int on) {
+  if (!h) return -1;
+  h->profile = on != 0;
+  h->ev_used = 0;
+  return 0;
+}
+
+int dinoseg_profile_num_kinds(void) { return K_COUNT; }
+const char* dinoseg_profile_kind_name(int kind) { return (kind >= 0 && kind < K_COUNT) ? kKindNames[kind] : ""; }
+
+int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds) {
+  if (!h || !ms_by_kind || !launches_by_kind || n_kinds < K_COUNT) return -1;
+  for (int k = 0; k < K_COUNT; ++k) { ms_by_kind[k] = 0.f; launches_by_kind[k] = 0; }
+  for (int i = 0; i < h->ev_used; ++i) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(h->ev[2 * i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]);
+    if (e != cudaSuccess) DSG_FAIL(h, "dinoseg_profile_read: %s", cudaGetErrorString(e));
+    ms_by_kind[h->ev_kind[i]] += ms;
+    launches_by_kind[h->ev_kind[i]] += 1;
+  }
+  h->ev_used = 0;
+  return 0;
+}
+
 int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprobs, uint8_t* lowres, int64_t* labels,
                     void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return -1;
@@ -531,15 +586,20 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
   int n = 0;
   h->launches = 0;
   const int stop = h->debug_stop;
+  if (!h->profile) h->ev_used = 0;
 
   // ---- prepare_tokens (vision_transformer.py:224-235) ----
-  DSG_CUDA(h, launch_im2col(frames, h->hid, batch, h->g, s)); ++n;
-  cls_row_kernel<<<(batch * D + 255) / 256, 256, 0, s>>>(h->cls, h->pos, h->x, batch, h->Ntok, D);
-  DSG_CUDA(h, cudaGetLastError()); ++n;
+  { LaunchScope ls(h, K_IM2COL, s); DSG_CUDA(h, launch_im2col(frames, h->hid, batch, h->g, s)); ++n; }
+  {
+    LaunchScope ls(h, K_CLS, s);
+    cls_row_kernel<<<(batch * D + 255) / 256, 256, 0, s>>>(h->cls, h->pos, h->x, batch, h->Ntok, D);
+    DSG_CUDA(h, cudaGetLastError()); ++n;
+  }
   {
     GemmParams p{};
     p.M = batch * h->P; p.N = D; p.K = 192; p.bias = h->pe_b; p.out = h->x; p.ldo = D;
     p.pos = h->pos; p.P = h->P; p.Ntok = h->Ntok;
+    LaunchScope ls(h, K_GEMM_PATCH, s);
     DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, h->tm_im2col, h->tm_pe, p, s)); ++n;
   }
   if (stop == 1) { h->launches = n; return 0; }
@@ -547,45 +607,51 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
   // ---- transformer blocks (vision_transformer.py:122-140) ----
   for (int i = 0; i < h->cfg.n_blocks; ++i) {
     BlockW& b = h->blocks[i];
-    DSG_CUDA(h, launch_layernorm(h->x, b.ln1_g, b.ln1_b, h->abuf, M, D, eps, s)); ++n;
+    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, b.ln1_g, b.ln1_b, h->abuf, M, D, eps, s)); ++n; }
     {
       GemmParams p{};
       p.M = M; p.N = 3 * D; p.K = D; p.bias = b.qkv_b; p.out = h->qkv; p.ldo = 3 * D;
       p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
+      LaunchScope ls(h, K_GEMM_QKV, s);
       DSG_CUDA(h, launch_gemm(EPI_BF16, h->tm_abuf, b.tm_qkv, p, s)); ++n;
     }
     if (stop == 2 + 3 * i) { h->launches = n; return 0; }
     {
       AttnParams p{};
       p.B = batch; p.H = H; p.N = h->Ntok; p.D = D; p.out = h->abuf;
+      LaunchScope ls(h, K_ATTN, s);
       DSG_CUDA(h, launch_attention(h->tm_qkv3d, p, s)); ++n;
     }
     {
       GemmParams p{};
       p.M = M; p.N = D; p.K = D; p.bias = b.proj_b; p.out = h->x; p.ldo = D;
+      LaunchScope ls(h, K_GEMM_PROJ, s);
       DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_abuf, b.tm_proj, p, s)); ++n;
     }
     if (stop == 3 + 3 * i) { h->launches = n; return 0; }
-    DSG_CUDA(h, launch_layernorm(h->x, b.ln2_g, b.ln2_b, h->abuf, M, D, eps, s)); ++n;
+    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, b.ln2_g, b.ln2_b, h->abuf, M, D, eps, s)); ++n; }
     {
       GemmParams p{};
       p.M = M; p.N = HID; p.K = D; p.bias = b.fc1_b; p.out = h->hid; p.ldo = HID;
+      LaunchScope ls(h, K_GEMM_FC1, s);
       DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, h->tm_abuf, b.tm_fc1, p, s)); ++n;
     }
     {
       GemmParams p{};
       p.M = M; p.N = D; p.K = HID; p.bias = b.fc2_b; p.out = h->x; p.ldo = D;
+      LaunchScope ls(h, K_GEMM_FC2, s);
       DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_hid, b.tm_fc2, p, s)); ++n;
     }
     if (stop == 4 + 3 * i) { h->launches = n; return 0; }
   }
 
   // ---- final norm + head (vision_transformer.py:243, pl_torch_modules.py:243-255) ----
-  DSG_CUDA(h, launch_layernorm(h->x, h->norm_g, h->norm_b, h->abuf, M, D, eps, s)); ++n;
+  { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, h->norm_g, h->norm_b, h->abuf, M, D, eps, s)); ++n; }
   float* h1 = reinterpret_cast<float*>(h->hid);
   {
     GemmParams p{};
     p.M = M; p.N = h->cfg.head_h1; p.K = D; p.bias = h->h1_b; p.out = h1; p.ldo = h->cfg.head_h1;
+    LaunchScope ls(h, K_GEMM_HEAD, s);
     DSG_CUDA(h, launch_gemm(EPI_RELU_F32, h->tm_abuf, h->tm_h1, p, s)); ++n;
   }
   uint8_t* lr = lowres ? lowres : h->lowres_ws;
@@ -598,11 +664,12 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
     }
     const int ntiles = (batch * h->P + HT_ROWS - 1) / HT_ROWS;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
+    LaunchScope ls(h, K_HEAD_TAIL, s);
     head_tail_kernel<<<grid, 256, smem, s>>>(h1, h->w2t, h->b2, h->w3, h->b3, logprobs, lr, batch, h->P, h->Ntok,
                                              h->cfg.head_h1, h->cfg.head_h2, h->cfg.n_classes);
     DSG_CUDA(h, cudaGetLastError()); ++n;
   }
-  if (labels) { DSG_CUDA(h, launch_replicate(lr, labels, batch, h->g, h->p_rep, s)); ++n; }
+  if (labels) { LaunchScope ls(h, K_REPLICATE, s); DSG_CUDA(h, launch_replicate(lr, labels, batch, h->g, h->p_rep, s)); ++n; }
   h->launches = n;
   return 0;
 }

@@ -1,0 +1,399 @@
+"""Host side of the drop-in: `DINOSeg` with the reference's method surface
+(`load_from_checkpoint`, `set_resolution`, `predict`, `forward`; reference
+dt_segmentation/src/pl_torch_modules.py:141-300), executing on libdinoseg.so.
+
+PyTorch is used for what it is good at here — owning device memory (parameters, workspace,
+outputs) and streams.  All arithmetic of the hot path happens inside the CUDA library; there is
+no eager / CPU fallback: calling forward on a CPU model raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import io
+import pickle
+import types
+import warnings
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .synthetic import ARCHS
+from .transforms import get_transforms
+
+
+# ------------------------------------------------------------------------------------------
+# Parameter containers with the reference's state_dict names (vision_transformer.py:163-191).
+# They are never called: they only hold tensors (and give PyTorch's default initialisers, which
+# is what the reference relies on for the conv and the head).
+# ------------------------------------------------------------------------------------------
+class _Attention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attention(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim, hidden)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, dim, patch):
+        super().__init__()
+        self.patch_size = patch
+        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+
+
+class _Backbone(nn.Module):
+    """Parameters of the truncated DINO ViT (first n_blocks blocks, pl_torch_modules.py:177)."""
+
+    def __init__(self, dim, hidden, num_heads, n_blocks, patch=8, img_size=224):
+        super().__init__()
+        self.embed_dim = dim
+        self.num_heads = num_heads
+        self.patch_embed = _PatchEmbed(dim, patch)
+        n_pos = (img_size // patch) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n_pos + 1, dim))
+        self.blocks = nn.ModuleList([_Block(dim, hidden) for _ in range(n_blocks)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        # reference init (vision_transformer.py:188-200); Conv2d keeps its default init
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+
+class _MLPHead(nn.Module):
+    """pl_torch_modules.py:108-124."""
+
+    def __init__(self, n_classes, input_dim):
+        super().__init__()
+        self.layer_1 = nn.Linear(input_dim, 200)
+        self.layer_2 = nn.Linear(200, 100)
+        self.layer_3 = nn.Linear(100, n_classes)
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    """PL checkpoints pickle ctor kwargs (optimizer class, loggers...).  Classes from packages
+    that are not installed are replaced by inert placeholders instead of failing the load."""
+
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except Exception:
+            return type(name, (), {"__init__": lambda self, *a, **k: None,
+                                   "__setstate__": lambda self, s: None})
+
+
+_tolerant_pickle = types.ModuleType("dino_b200_tolerant_pickle")
+_tolerant_pickle.Unpickler = _TolerantUnpickler
+_tolerant_pickle.load = lambda f, **kw: _TolerantUnpickler(f, **kw).load()
+_tolerant_pickle.__name__ = "pickle"
+
+
+class DINOSeg(nn.Module):
+    """DINO ViT-S/8 (or ViT-B/8) truncated to `n_blocks` blocks + per-patch MLP head.
+
+    Constructor arguments are the reference's (pl_torch_modules.py:144-147); the training-only
+    ones are accepted and stored, nothing else.  `arch` ('vit_small' | 'vit_base') is an
+    extension: the reference hard-codes ViT-S.
+    """
+
+    def __init__(self, data_path=None, write_path=None, class_names=None, head='linear', n_blocks=1,
+                 batch_size=1, lr=1e-6, optimizer=None, freeze_backbone=True, max_epochs=200, patience=10,
+                 grayscale=False, n_classes=7, pretrain_on_sim=False, comet_logger=None, augmented=True,
+                 random_init=False, backbone='vit', arch='vit_small'):
+        super().__init__()
+        if backbone != 'vit':
+            raise NotImplementedError("only backbone='vit' is part of the B200 hot path (cnn1/cnn2 are ablations)")
+        if head != 'mlp':
+            raise NotImplementedError("only head='mlp' is implemented on the B200 path "
+                                      "(every shipped configuration of the reference uses it)")
+        if arch not in ARCHS:
+            raise ValueError(f"unknown arch {arch!r}")
+        self.n_blocks = n_blocks
+        self.head = head
+        self.batch_size = batch_size
+        self.lr = lr
+        self.optimizer = optimizer
+        self.freeze_backbone = freeze_backbone
+        self.max_epochs = max_epochs
+        self.patience = patience
+        self.grayscale = grayscale
+        self.n_classes = n_classes
+        self.comet_logger = comet_logger
+        self.class_names = class_names
+        self.pretrain_on_sim = pretrain_on_sim
+        self.augmented = augmented
+        self.random_init = random_init
+        self.backbone = backbone
+        self.arch = arch
+        self.hparams = dict(data_path=data_path, write_path=write_path, class_names=class_names, head=head,
+                            n_blocks=n_blocks, batch_size=batch_size, lr=lr, freeze_backbone=freeze_backbone,
+                            max_epochs=max_epochs, patience=patience, grayscale=grayscale, n_classes=n_classes,
+                            pretrain_on_sim=pretrain_on_sim, augmented=augmented, random_init=random_init,
+                            backbone=backbone, arch=arch)
+
+        a = ARCHS[arch]
+        self.mlp_input_dim = a["embed_dim"]
+        self.resolution = 480
+        self.transforms = get_transforms(self.resolution)
+        # The reference downloads the pretrained DINO weights here (dt_utils.py:19-29).  There is no
+        # network: parameters start from the reference's random init and are expected to be
+        # overwritten by load_from_checkpoint / load_state_dict.
+        self.dino = _Backbone(a["embed_dim"], a["mlp_hidden"], a["num_heads"], n_blocks)
+        self.clf = _MLPHead(n_classes, a["embed_dim"])
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+        self._handle = None
+        self._handle_device = None
+        self._fingerprint = None
+        self._lib_res = None
+        self._workspace = None
+
+    # -------------------------------------------------------------------------------------
+    # construction from a checkpoint (replaces LightningModule.load_from_checkpoint, README.md:31)
+    # -------------------------------------------------------------------------------------
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+        try:
+            ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        except Exception:
+            with open(checkpoint_path, "rb") as f:
+                ckpt = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=False,
+                                  pickle_module=_tolerant_pickle)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(kwargs)
+        allowed = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
+        hp = {k: v for k, v in hp.items() if k in allowed}
+        sd = ckpt["state_dict"]
+        if "arch" not in hp and "dino.cls_token" in sd:
+            hp["arch"] = "vit_base" if sd["dino.cls_token"].shape[-1] == 768 else "vit_small"
+        model = cls(**hp)
+        model.load_state_dict(sd, strict=strict)
+        if map_location is not None:
+            model = model.to(map_location)
+        return model
+
+    # -------------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.dino.cls_token.device
+
+    def set_resolution(self, resolution=480):
+        """pl_torch_modules.py:270-274."""
+        if resolution % 8 != 0:
+            raise ValueError('Resolution should be a multiple of 8.')
+        self.transforms = get_transforms(resolution)
+        self.resolution = resolution
+
+    # -------------------------------------------------------------------------------------
+    # library handle management
+    # -------------------------------------------------------------------------------------
+    def _cfg(self):
+        a = ARCHS[self.arch]
+        return _lib.DinosegCfg(a["embed_dim"], a["num_heads"], a["mlp_hidden"], self.n_blocks, 8,
+                               int(round((self.dino.pos_embed.shape[1] - 1) ** 0.5)), self.n_classes, 200, 100, 0,
+                               1e-6)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {_lib.last_error(self._handle)}")
+
+    def _release(self):
+        if self._handle is not None:
+            try:
+                _lib.load().dinoseg_destroy(self._handle)
+            except Exception:
+                pass
+        self._handle = None
+        self._fingerprint = None
+        self._lib_res = None
+        self._workspace = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def _ensure_handle(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("DINOSeg (B200 build) runs on CUDA only: move the model with .to('cuda:N'); "
+                               "there is no CPU fallback")
+        lib = _lib.load()
+        if self._handle is None or self._handle_device != dev:
+            self._release()
+            h = C.c_void_p()
+            cfg = self._cfg()
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            if lib.dinoseg_create(C.byref(cfg), idx, C.byref(h)) != 0:
+                raise RuntimeError("dinoseg_create failed: " + _lib.last_error(None))
+            self._handle, self._handle_device = h, dev
+        sd = self.state_dict()
+        fp = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        if fp != self._fingerprint:
+            stream = self._stream()
+            for k, v in sd.items():
+                t = v.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                self._check(lib.dinoseg_set_weight(self._handle, k.encode(), t.data_ptr(), shape, t.dim(), stream),
+                            f"dinoseg_set_weight({k})")
+            torch.cuda.current_stream(dev).synchronize()  # staging copies `t` may be temporaries
+            self._fingerprint = fp
+            self._lib_res = None
+        return lib
+
+    def _ensure_resolution(self, lib, res):
+        if self._lib_res != res:
+            rc = lib.dinoseg_set_resolution(self._handle, int(res), self._stream())
+            if rc != 0:
+                msg = _lib.last_error(self._handle)
+                if "multiple of 8" in msg:
+                    raise ValueError(msg)
+                raise RuntimeError("dinoseg_set_resolution failed: " + msg)
+            self._lib_res = res
+            self._workspace = None
+
+    def _ensure_workspace(self, lib, batch):
+        need = lib.dinoseg_workspace_bytes(self._handle, batch)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # -------------------------------------------------------------------------------------
+    # inference
+    # -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def infer(self, x, want_logprobs=True, want_lowres=False, want_labels=False):
+        """Run the hot path on device frames x: fp32 [B,3,r,r] (normalised).
+
+        Returns (logprobs [B*P,C] f32 | None, lowres [B,g,g] u8 | None, labels [B,g*p,g*p] i64 | None),
+        all device tensors; asynchronous on the current stream."""
+        lib = self._ensure_handle()
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise ValueError(f"expected frames of shape [B,3,r,r], got {tuple(x.shape)}")
+        if x.device != self.device:
+            raise ValueError(f"frames are on {x.device}, model on {self.device}")
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        b, res = int(x.shape[0]), int(x.shape[2])
+        self._ensure_resolution(lib, res)
+        ws = self._ensure_workspace(lib, b)
+        g = res // 8
+        p = 480 // g
+        dev = self.device
+        lp = torch.empty((b * g * g, self.n_classes), dtype=torch.float32, device=dev) if want_logprobs else None
+        low = torch.empty((b, g, g), dtype=torch.uint8, device=dev) if want_lowres else None
+        lab = torch.empty((b, g * p, g * p), dtype=torch.int64, device=dev) if want_labels else None
+        rc = lib.dinoseg_forward(self._handle, x.data_ptr(), b,
+                                 lp.data_ptr() if lp is not None else None,
+                                 low.data_ptr() if low is not None else None,
+                                 lab.data_ptr() if lab is not None else None,
+                                 ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, "dinoseg_forward")
+        return lp, low, lab
+
+    def forward(self, x):
+        """pl_torch_modules.py:239-256: [B,3,r,r] -> per-patch log-probabilities [B*P, C]."""
+        return self.infer(x, want_logprobs=True)[0]
+
+    def predict(self, x):
+        """Run inference on a single image (pl_torch_modules.py:276-300).
+
+        x : PIL.Image (or HxWx3 uint8 array).  Returns an int64 ndarray of shape
+        [g*p, g*p] (480x480 for resolutions 240/480/960)."""
+        img = self.transforms(image=np.array(x))['image']
+        frames = img.unsqueeze(0).to(self.device)
+        _, _, lab = self.infer(frames, want_logprobs=False, want_labels=True)
+        return lab[0].cpu().numpy()
+
+    def predict_batch(self, frames, output="labels"):
+        """Batched counterpart of predict() for already-normalised frames [B,3,r,r].
+
+        Device frames -> device result (asynchronous).  Host frames (ideally pinned) go through
+        the library's host entry point, which copies in, runs, copies out and synchronises ->
+        numpy result.  output: 'labels' (int64 [B,g*p,g*p]) or 'lowres' (uint8 [B,g,g])."""
+        if output not in ("labels", "lowres"):
+            raise ValueError(output)
+        if frames.device.type == "cuda":
+            _, low, lab = self.infer(frames, want_logprobs=False, want_lowres=output == "lowres",
+                                     want_labels=output == "labels")
+            return lab if output == "labels" else low
+        lib = self._ensure_handle()
+        frames = frames.contiguous().float()
+        b, res = int(frames.shape[0]), int(frames.shape[2])
+        self._ensure_resolution(lib, res)
+        g = res // 8
+        p = 480 // g
+        pin = torch.cuda.is_available()
+        low = torch.empty((b, g, g), dtype=torch.uint8, pin_memory=pin) if output == "lowres" else None
+        lab = torch.empty((b, g * p, g * p), dtype=torch.int64, pin_memory=pin) if output == "labels" else None
+        rc = lib.dinoseg_predict_host(self._handle, frames.data_ptr(), b,
+                                      low.data_ptr() if low is not None else None,
+                                      lab.data_ptr() if lab is not None else None, self._stream())
+        self._check(rc, "dinoseg_predict_host")
+        return (lab if output == "labels" else low).numpy()
+
+    def profile_enable(self, on=True):
+        """Bracket every kernel launch of the following forwards with CUDA events."""
+        lib = self._ensure_handle()
+        self._check(lib.dinoseg_profile_enable(self._handle, 1 if on else 0), "dinoseg_profile_enable")
+
+    def profile_read(self):
+        """-> {kernel kind: (total ms, launches)} accumulated since enable / the last read."""
+        lib = self._ensure_handle()
+        n = lib.dinoseg_profile_num_kinds()
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        self._check(lib.dinoseg_profile_read(self._handle, ms, cnt, n), "dinoseg_profile_read")
+        return {lib.dinoseg_profile_kind_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
+
+    def last_launch_count(self):
+        return _lib.load().dinoseg_last_launch_count(self._handle) if self._handle is not None else 0
+
+    # -------------------------------------------------------------------------------------
+    # training side of the reference: out of scope of this build
+    # -------------------------------------------------------------------------------------
+    def fit(self, *a, **k):
+        raise NotImplementedError("training is out of scope of the B200 inference build")
+
+    def freeze_bb(self):
+        for p in self.dino.parameters():
+            p.requires_grad = False
+
+    def unfreeze_bb(self):
+        warnings.warn("the B200 build is inference-only; gradients are never computed")

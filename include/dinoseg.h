@@ -96,6 +96,14 @@ int64_t dinoseg_copy_buffer(dinoseg_t* h, const char* name, void* dst, size_t ds
 int dinoseg_set_debug_stop(dinoseg_t* h, int stage);
 /* number of kernels launched by the last dinoseg_forward */
 int dinoseg_last_launch_count(const dinoseg_t* h);
+/* Per-kernel-kind device timing: when enabled, every launch of the following forwards is
+ * bracketed by a pair of cudaEvents on the launching stream; dinoseg_profile_read waits for
+ * them, sums the elapsed milliseconds and launch counts per kind (since enable / last read)
+ * and resets the accumulation. */
+int dinoseg_profile_enable(dinoseg_t* h, int on);
+int dinoseg_profile_num_kinds(void);
+const char* dinoseg_profile_kind_name(int kind);
+int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds);
 
 /* ---- kernel-level entry points (parity tests of the individual CUDA kernels) ----------- */
 /* C[M,N] = A[M,K] bf16 x W[N,K]^T bf16 with epilogue `epi` (see csrc/gemm.cuh EPI_*) */
