@@ -238,6 +238,7 @@ struct dinoseg {
 
   // optional per-kernel-kind timing (cudaEvents around every launch of a forward)
   bool profile = false;
+  uint32_t profile_mask = 0xffffffffu;  // bit k set = kind k gets its pair of events
   std::vector<cudaEvent_t> ev;       // 2 per launch slot
   std::vector<int> ev_kind;          // kind of each recorded launch
   int ev_used = 0;
@@ -329,7 +330,7 @@ const char* const kKindNames[K_COUNT] = {"im2col", "cls_row", "gemm_patch", "lay
 struct LaunchScope {
   dinoseg* h; cudaStream_t s; int slot;
   LaunchScope(dinoseg* h_, int kind, cudaStream_t s_) : h(h_), s(s_), slot(-1) {
-    if (!h->profile) return;
+    if (!h->profile || !((h->profile_mask >> kind) & 1u)) return;
     slot = h->ev_used++;
     while (int(h->ev.size()) < 2 * (slot + 1)) {
       cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e);
@@ -543,6 +544,12 @@ int dinoseg_profile_enable(dinoseg_t* h, int on) {
   if (!h) return -1;
   h->profile = on != 0;
   h->ev_used = 0;
+  return 0;
+}
+
+int dinoseg_profile_set_mask(dinoseg_t* h, uint32_t kind_mask) {
+  if (!h) return -1;
+  h->profile_mask = kind_mask;
   return 0;
 }
 

@@ -368,9 +368,17 @@ class DINOSeg(nn.Module):
         self._check(rc, "dinoseg_predict_host")
         return (lab if output == "labels" else low).numpy()
 
-    def profile_enable(self, on=True):
-        """Bracket every kernel launch of the following forwards with CUDA events."""
+    def profile_enable(self, on=True, kinds=None):
+        """Bracket kernel launches of the following forwards with CUDA events (on the launching
+        stream).  kinds: iterable of kernel-kind names to restrict the events to (None = all)."""
         lib = self._ensure_handle()
+        mask = 0xffffffff
+        if kinds is not None:
+            names = [lib.dinoseg_profile_kind_name(i).decode() for i in range(lib.dinoseg_profile_num_kinds())]
+            mask = 0
+            for k in kinds:
+                mask |= 1 << names.index(k)
+        self._check(lib.dinoseg_profile_set_mask(self._handle, mask), "dinoseg_profile_set_mask")
         self._check(lib.dinoseg_profile_enable(self._handle, 1 if on else 0), "dinoseg_profile_enable")
 
     def profile_read(self):

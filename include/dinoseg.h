@@ -101,6 +101,8 @@ int dinoseg_last_launch_count(const dinoseg_t* h);
  * them, sums the elapsed milliseconds and launch counts per kind (since enable / last read)
  * and resets the accumulation. */
 int dinoseg_profile_enable(dinoseg_t* h, int on);
+/* restrict the events to the kinds whose bit is set (default: all kinds) */
+int dinoseg_profile_set_mask(dinoseg_t* h, uint32_t kind_mask);
 int dinoseg_profile_num_kinds(void);
 const char* dinoseg_profile_kind_name(int kind);
 int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds);

@@ -1,0 +1,199 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol declared
+in include/dinoseg.h, the Python surface mirrors the reference's (names, arguments, errors), the
+product path never falls back to the CPU, and the frame sharding used for N > 1 GPUs is right
+(world_size-2 gloo run)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from dino_b200 import DINOSeg, _lib, dist, synthetic
+from dino_b200 import build as B
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "dinoseg.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dinoseg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = B.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dinoseg.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes prototypes and the header disagree"
+
+
+def test_library_contains_blackwell_sass():
+    """tcgen05 / TMA must be in the SASS of the shipped library (no mma.sync path)."""
+    path = B.build()
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out or "UTCMMA" in out or "UTC" in out
+    assert "UTMALDG" in out
+    assert "LDTM" in out
+    assert "HMMA" not in out.replace("UTCHMMA", "")
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
+
+
+def test_create_fails_without_gpu_instead_of_falling_back():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    cfg = _lib.DinosegCfg(384, 6, 1536, 1, 8, 28, 7, 200, 100, 0, 1e-6)
+    h = ctypes.c_void_p()
+    assert lib.dinoseg_create(ctypes.byref(cfg), 0, ctypes.byref(h)) != 0
+    assert "no CUDA device" in _lib.last_error(None) or "CPU" in _lib.last_error(None)
+
+
+def test_forward_on_cpu_model_raises():
+    m = DINOSeg(head="mlp", n_blocks=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 64, 64))
+
+
+def test_set_resolution_semantics():
+    """pl_torch_modules.py:270-274."""
+    m = DINOSeg(head="mlp", n_blocks=1)
+    assert m.resolution == 480
+    m.set_resolution(240)
+    assert m.resolution == 240 and m.transforms.resolution == 240
+    with pytest.raises(ValueError, match="Resolution should be a multiple of 8."):
+        m.set_resolution(250)
+    assert m.resolution == 240
+
+
+def test_state_dict_keys_and_shapes_match_reference_inventory():
+    """SURVEY.md §3.1 state-dict inventory (n_blocks=3, MLP head, 7 classes)."""
+    m = DINOSeg(head="mlp", n_blocks=3, n_classes=7)
+    sd = m.state_dict()
+    ref = synthetic.init_state_dict(synthetic.make_config("vit_small", 3, 7))
+    assert list(sd.keys()) == list(ref.keys()) or sorted(sd.keys()) == sorted(ref.keys())
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    assert sd["dino.pos_embed"].shape == (1, 785, 384)
+    assert sum(v.numel() for v in sd.values()) == 5_796_091 or abs(sum(v.numel() for v in sd.values()) - 5.80e6) < 2e4
+
+
+def test_load_from_checkpoint_roundtrip(tmp_path):
+    """PL-style checkpoint: {'state_dict', 'hyper_parameters'}; hyper-parameters
+    of the training side (optimizer class, loggers) are accepted and ignored."""
+    cfg = synthetic.make_config("vit_small", 2, 5)
+    sd = synthetic.init_state_dict(cfg, 3, "trained_like")
+    hp = dict(data_path="d", write_path="w", class_names=None, head="mlp", n_blocks=2, batch_size=1, lr=1e-6,
+              optimizer=torch.optim.AdamW, freeze_backbone=True, max_epochs=200, patience=10, grayscale=False,
+              n_classes=5, pretrain_on_sim=False, comet_logger=None, augmented=True, random_init=False, backbone="vit")
+    path = tmp_path / "m.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": hp, "epoch": 3}, path)
+    m = DINOSeg.load_from_checkpoint(str(path))
+    assert m.n_blocks == 2 and m.n_classes == 5 and m.head == "mlp"
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    bad = dict(sd)
+    bad.pop("clf.layer_3.bias")
+    torch.save({"state_dict": bad, "hyper_parameters": hp}, path)
+    with pytest.raises(RuntimeError):
+        DINOSeg.load_from_checkpoint(str(path))
+
+
+def test_unsupported_variants_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        DINOSeg(head="mlp", backbone="cnn1")
+    with pytest.raises(NotImplementedError):
+        DINOSeg(head="mlp").fit()
+
+
+def test_drop_in_import_path():
+    import dt_segmentation
+    assert dt_segmentation.DINOSeg is DINOSeg
+    assert callable(dt_segmentation.parse_class_names)
+
+
+def test_transforms_restatement():
+    """Resize(INTER_LINEAR) -> Normalize(ImageNet) -> CHW (pl_torch_modules.py:33-41)."""
+    from dino_b200.transforms import get_transforms, IMAGENET_MEAN, IMAGENET_STD
+    img = synthetic.make_image_u8(480, 640, 3)
+    out = get_transforms(240)(image=img)["image"]
+    assert out.shape == (3, 240, 240) and out.dtype == torch.float32
+    same = get_transforms(480)(image=img[:, :480])["image"]
+    ref = (img[:, :480].astype(np.float32) / 255.0 - np.array(IMAGENET_MEAN, np.float32)) / np.array(IMAGENET_STD, np.float32)
+    assert np.abs(same.numpy() - ref.transpose(2, 0, 1)).max() < 1e-5
+
+
+@pytest.mark.parametrize("total,world", [(512, 8), (64, 1), (10, 4), (3, 8), (0, 2)])
+def test_shard_range_partitions(total, world):
+    spans = [dist.shard_range(total, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 == b0 and a1 >= a0
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch
+from dino_b200 import dist as D, synthetic
+rank, local, world = D.init(backend="gloo")
+lo, hi = D.shard_range(10, rank, world)
+frames = synthetic.make_frames(10, 16, seed=1)[lo:hi]
+D.barrier()
+s = D.sum_over_ranks(float(frames.double().sum()))
+n = D.sum_over_ranks(hi - lo)
+m = D.max_over_ranks(float(rank + 1))
+if rank == 0:
+    tot = float(synthetic.make_frames(10, 16, seed=1).double().sum())
+    print(json.dumps({"ok": abs(s - tot) < 1e-6 and n == 10 and m == world, "world": world}))
+D.barrier(); D.shutdown()
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """N > 1 path on CPU: world_size 2, gloo, frames sharded by rank, no data-path collective."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", str(script), ROOT]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    import json
+    r = json.loads(line)
+    assert r["ok"] and r["world"] == 2
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the reference-arm keys (tiny config)."""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--res", "64", "--n-blocks", "1", "--batch", "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert r["impl"] == "reference" and r["unit"] == "frames/s" and r["value"] > 0
+    assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1
+    assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["value"] == r["value"]
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under dino_b200/ or dt_segmentation/ may use it."""
+    for pkg in ("dino_b200", "dt_segmentation"):
+        for dp, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    with open(os.path.join(dp, f)) as fh:
+                        src = fh.read()
+                    assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                    assert "dinoseg_oracle" not in src, f

@@ -217,7 +217,21 @@ def _checks():
         "attn_2tiles": lambda: check_attention("attn_2tiles", 1, 256, 1),
         "attn_901": lambda: check_attention("attn_901", 2, 901, 6),
         "attn_3601": lambda: check_attention("attn_3601", 1, 3601, 6),
+        "attn_vitb_901": lambda: check_attention("attn_vitb_901", 1, 901, 12),
     }
+
+
+def check_names():
+    return [
+        "layernorm_384", "layernorm_768", "posembed_30", "posembed_60", "posembed_28", "posembed_vitb_60", "im2col",
+        "argmax_replicate", "argmax_replicate_odd", "gemm_tile", "gemm_k384", "gemm_qkv", "gemm_gelu",
+        "gemm_resid_k1536", "gemm_patch", "gemm_head", "gemm_big", "attn_1tile", "attn_ragged_small", "attn_2tiles",
+        "attn_901", "attn_3601", "attn_vitb_901",
+    ]
+
+
+def run_check(name):
+    return _checks()[name]()
 
 
 def main():
