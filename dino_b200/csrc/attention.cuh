@@ -3,21 +3,34 @@
 //
 //   S = (q*dh^-0.5) k^T ; P = softmax_rows(S) ; O = P v          per (frame b, head h)
 //
-// The reference materialises S and P ([B,H,N,N] fp32, 311 MB/frame/block at 480 px); here a
-// CTA owns one 128-query tile of one (b,h), streams 128-key K/V tiles through shared memory
-// with TMA, keeps S (128x128 fp32), P (bf16, aliasing S) and the running O (128x64 fp32) in
-// TMEM, and never writes N x N data anywhere.
+// The reference materialises S and P ([B,H,N,N] fp32, 311 MB/frame/block at 480 px); here S, P and
+// the running O only ever exist in TMEM and nothing N x N is written anywhere.
 //
-// q/k/v are read straight out of the qkv GEMM output [B, N, 3*D] bf16 (column =
-// which*D + h*64 + d, exactly nn.Linear's output order, reference :82) through ONE 3-D tensor
-// map {3D, N, B}; rows >= N of a frame are zero-filled by TMA.  q is pre-scaled by dh^-0.5
-// (exact in bf16: 0.125) by the qkv epilogue.
+// q/k/v are read straight out of the qkv GEMM output [B, N, 3*D] bf16 (column = which*D + h*64 + d,
+// exactly nn.Linear's output order, reference :82) through ONE 3-D tensor map {3D, N, B}; rows >= N
+// of a frame are zero-filled by TMA.  q is pre-scaled by dh^-0.5 (exact in bf16: 0.125) by the qkv
+// GEMM epilogue.
 //
-// Warp roles (192 threads, 2 CTAs resident per SM so one CTA's softmax overlaps the other's MMAs):
-//   warp 0     : TMA producer (Q once; K,V ring)
-//   warp 1     : TMEM alloc + tcgen05.mma issuer:  S = Q K^T (SS, K-major both) ; O += P V (TS: P from
-//                TMEM, V as an MN-major smem operand — no transpose of V is ever made)
-//   warps 2..5 : online softmax, one query row per thread (tcgen05.ld 32x32b), O rescale, epilogue
+// Work decomposition: a work item is a pair of 128-query tiles (256 queries) of one (b,h).  The
+// kernel is persistent (grid = #SMs, item = blockIdx.x + k*gridDim.x) and streams the 128-key K/V
+// tiles of the item through a shared-memory ring.
+//
+// Warp roles (384 threads, 1 CTA/SM, all 512 TMEM columns):
+//   warp 0      : TMA producer (Q pair per item; K,V ring)
+//   warp 1      : TMEM alloc + single-thread tcgen05.mma issuer
+//                   S_t = Q_t K^T          (SS, both K-major)            t = 0,1
+//                   O_t += P_t V           (TS: P from TMEM, V MN-major: V is never transposed)
+//                 S_t, P_t and O_t have their OWN TMEM columns (2x128 + 2x64 + 2x64 = 512), so
+//                 QK_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers
+//                 (s_empty), long before P_t(j) exists: the softmax warps never wait for the tensor
+//                 pipe.  Issue order per key tile j:  QK0(j+1) QK1(j+1) PV0(j) PV1(j).
+//   warps 2,3   : idle (they only complete the producer warpgroup for setmaxnreg)
+//   warps 4..7  : softmax of query tile 0, one query row per thread (tcgen05.ld 32x32b)
+//   warps 8..11 : softmax of query tile 1
+// The exponentials are the bottleneck at head_dim 64 (16 MUFU.EX2 per clock per SM vs 8192 tensor
+// flop per clock): the two softmax warpgroups keep the MUFU pipe busy back to back; the running
+// maximum is only raised when it grows by more than 2^8 (lazy rescale), so the O accumulator is
+// almost never touched between PV MMAs.
 #pragma once
 #include "ptx.cuh"
 
@@ -27,58 +40,68 @@ struct AttnParams {
   int B, H, N;          // frames, heads, tokens per frame
   int D;                // embed dim (= H*64)
   __nv_bfloat16* out;   // [B*N, D], column = h*64 + d   (reference :104 transpose(1,2).reshape)
+  int qpairs;           // ceil(N / 256)
+  int num_items;        // B * H * qpairs
 };
 
-constexpr int ATT_BM = 128;     // queries per CTA
+constexpr int ATT_BM = 128;     // queries per tile (two tiles per work item)
 constexpr int ATT_BN = 128;     // keys per tile
 constexpr int ATT_DH = 64;      // head dim
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 384;
 constexpr int ATT_TILE_BYTES = 128 * ATT_DH * 2;  // 16 KB (Q, K or V tile)
 
 template <int KV_STAGES>
 constexpr size_t attn_smem_bytes() {
-  return size_t(1 + 2 * KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
+  return size_t(2 + 2 * KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 }
 
+__device__ __forceinline__ void setmaxnreg_dec_80() { asm volatile("setmaxnreg.dec.sync.aligned.u32 80;"); }
+__device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
+
 template <int KV_STAGES>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  constexpr uint32_t TMEM_COLS = 256;
-  constexpr uint32_t S_COL = 0;     // S: 128 fp32 columns; P (bf16x2) aliases columns [0,64)
-  constexpr uint32_t O_COL = 128;   // O: 64 fp32 columns
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t S_COL0 = 0;     // S_t: 128 fp32 columns at t*128
+  constexpr uint32_t P_COL0 = 256;   // P_t: 64 columns (128 bf16 keys, 2 per column) at 256 + t*64
+  constexpr uint32_t O_COL0 = 384;   // O_t: 64 fp32 columns at 384 + t*64
   constexpr float LOG2E = 1.4426950408889634f;
+  constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays <= 2^8
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
-  uint8_t* sQ = smem;
-  uint8_t* sKV = smem + ATT_TILE_BYTES;  // [stage][K 16KB | V 16KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(1 + 2 * KV_STAGES) * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint8_t* sQ = smem;                          // [2][16 KB]
+  uint8_t* sKV = smem + 2 * ATT_TILE_BYTES;    // [stage][K 16 KB | V 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(2 + 2 * KV_STAGES) * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* q_empty = bars + 1;                // 1
+  uint64_t* kv_full = bars + 2;                // KV_STAGES
+  uint64_t* kv_empty = kv_full + KV_STAGES;    // KV_STAGES
+  uint64_t* s_full = kv_empty + KV_STAGES;     // 2: S_t(j) written by the tensor pipe
+  uint64_t* s_empty = s_full + 2;              // 2 (128 arrivals each): S_t(j) is in registers
+  uint64_t* p_full = s_empty + 2;              // 2 (128 arrivals each): P_t(j) written, O_t rescaled
+  uint64_t* pv_done = p_full + 2;              // 2: PV_t(j) retired (P_t free again, O_t stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BM;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_done[t], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -87,141 +110,214 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQKV, q_full, h * ATT_DH, q0, b);
-      for (int j = 0; j < num_tiles; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
-        uint8_t* sk = sKV + size_t(s) * 2 * ATT_TILE_BYTES;
-        tma_load_3d(sk, &tmQKV, &kv_full[s], p.D + h * ATT_DH, j * ATT_BN, b);
-        tma_load_3d(sk + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.D + h * ATT_DH, j * ATT_BN, b);
+  if (warp < 4) {
+    setmaxnreg_dec_80();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      uint32_t kvc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int qp = item % p.qpairs;
+        const int bh = item / p.qpairs;
+        const int h = bh % p.H, b = bh / p.H;
+        const int q0 = qp * 2 * ATT_BM;
+        const bool two = q0 + ATT_BM < p.N;
+        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
+        mbar_expect_tx(q_full, two ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
+        tma_load_3d(sQ, &tmQKV, q_full, h * ATT_DH, q0, b);
+        if (two) tma_load_3d(sQ + ATT_TILE_BYTES, &tmQKV, q_full, h * ATT_DH, q0 + ATT_BM, b);
+        for (int j = 0; j < num_tiles; ++j, ++kvc) {
+          const int s = kvc % KV_STAGES;
+          mbar_wait(&kv_empty[s], ((kvc / KV_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
+          uint8_t* sk = sKV + size_t(s) * 2 * ATT_TILE_BYTES;
+          tma_load_3d(sk, &tmQKV, &kv_full[s], p.D + h * ATT_DH, j * ATT_BN, b);
+          tma_load_3d(sk + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.D + h * ATT_DH, j * ATT_BN, b);
+        }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0);  // K^T: K-major B
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_DH, 1);  // V  : MN-major B
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < num_tiles; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&kv_full[s], ph);
-        tc_fence_after();
-        const uint32_t sk = smem_u32(sKV + size_t(s) * 2 * ATT_TILE_BYTES);
+      const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ));
+      const uint64_t qdesc1 = umma_desc_sw128(smem_u32(sQ + ATT_TILE_BYTES));
+      uint32_t kvc = 0, c0 = 0, c1 = 0;   // c_t: key tiles of query tile t processed so far (barrier phases)
+      int it = 0;
+      auto issue_qk = [&](int t, uint32_t kv_counter) {
+        const uint32_t sk = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES);
         const uint64_t kdesc = umma_desc_sw128(sk);
-        const uint64_t vdesc = umma_desc_sw128(sk + ATT_TILE_BYTES);
-        // S = Q K^T : 4 x (128x128x16).  Tensor-pipe ordering guarantees this does not overwrite
-        // P(j-1) before the previously issued P(j-1) V(j-1) has read it.
+        const uint64_t qdesc = t ? qdesc1 : qdesc0;
 #pragma unroll
         for (int k = 0; k < ATT_DH / 16; ++k)
-          umma_ss(tmem_base + S_COL, qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk, k != 0);
-        tc_commit(s_full);
-        // wait for the softmax warps to publish P(j) (and the rescaled O)
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        // O += P V : 8 x (128x64x16); P: 8 TMEM columns per step; V: 16 keys = 2 KB per step
+          umma_ss(tmem_base + S_COL0 + uint32_t(t * 128), qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk,
+                  k != 0);
+        tc_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, uint32_t kv_counter, bool accumulate) {
+        const uint32_t sv = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
+        const uint64_t vdesc = umma_desc_sw128(sv);
+        // P: 8 TMEM columns (16 bf16 keys) per K step; V: 16 keys = 2 KB per K step
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(tmem_base + O_COL, tmem_base + S_COL + uint32_t(k * 8), vdesc + uint64_t(k * 128), idesc_pv,
-                  (j | k) != 0);
-        tc_commit(&kv_empty[s]);
+          umma_ts(tmem_base + O_COL0 + uint32_t(t * 64), tmem_base + P_COL0 + uint32_t(t * 64 + k * 8),
+                  vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+        tc_commit(&pv_done[t]);
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int qp = item % p.qpairs;
+        const bool two = qp * 2 * ATT_BM + ATT_BM < p.N;
+        mbar_wait(q_full, it & 1);
+        mbar_wait(&kv_full[kvc % KV_STAGES], (kvc / KV_STAGES) & 1);
+        tc_fence_after();
+        issue_qk(0, kvc);
+        if (two) issue_qk(1, kvc);
+        if (num_tiles == 1) tc_commit(q_empty);
+        for (int j = 0; j < num_tiles; ++j, ++kvc) {
+          const bool more = j + 1 < num_tiles;
+          if (more) {
+            // next scores as soon as the softmax warps hold the current ones in registers
+            mbar_wait(&kv_full[(kvc + 1) % KV_STAGES], ((kvc + 1) / KV_STAGES) & 1);
+            mbar_wait(&s_empty[0], c0 & 1);
+            tc_fence_after();
+            issue_qk(0, kvc + 1);
+            if (two) {
+              mbar_wait(&s_empty[1], c1 & 1);
+              tc_fence_after();
+              issue_qk(1, kvc + 1);
+            }
+            if (j + 2 == num_tiles) tc_commit(q_empty);  // last reads of Q0/Q1 have been issued
+          }
+          mbar_wait(&p_full[0], c0 & 1); ++c0;
+          tc_fence_after();
+          issue_pv(0, kvc, j != 0);
+          if (two) {
+            mbar_wait(&p_full[1], c1 & 1); ++c1;
+            tc_fence_after();
+            issue_pv(1, kvc, j != 0);
+          }
+          tc_commit(&kv_empty[kvc % KV_STAGES]);      // K(j), V(j) fully consumed once these MMAs retire
+        }
       }
-      tc_commit(o_full);
     }
   } else {
-    const int quarter = warp & 3;
+    // ------------------------------ softmax warpgroups ------------------------------
+    setmaxnreg_inc_208();
+    const int t = (warp - 4) >> 2;                 // query tile of this warpgroup
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
-    float m = -INFINITY;  // running row max of the raw (pre-log2e) scores
-    float l = 0.f;        // running row sum
+    const uint32_t s_addr = lane_base + S_COL0 + uint32_t(t * 128);
+    const uint32_t o_addr = lane_base + O_COL0 + uint32_t(t * 64);
+    const uint32_t p_addr = lane_base + P_COL0 + uint32_t(t * 64);
+    uint32_t sc = 0;                               // key tiles processed so far by this warpgroup
 
-    for (int j = 0; j < num_tiles; ++j) {
-      mbar_wait(s_full, j & 1);  // also implies P(j-1) V(j-1) retired: O is stable
-      tc_fence_after();
-      float s[128];
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int qp = item % p.qpairs;
+      const int bh = item / p.qpairs;
+      const int h = bh % p.H, b = bh / p.H;
+      const int q0 = qp * 2 * ATT_BM + t * ATT_BM;
+      if (q0 >= p.N) continue;                     // second tile of the last pair may be empty
+      float m = 0.f;                               // (stale) running row max of the raw scores
+      float l = 0.f;                               // running row sum of exp(s - m)
+
+      for (int j = 0; j < num_tiles; ++j, ++sc) {
+        mbar_wait(&s_full[t], sc & 1);
+        tc_fence_after();
+        float s[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(lane_base + S_COL + uint32_t(c * 32), r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
-      }
-      tmem_ld_wait();
-      const int kbase = j * ATT_BN;
-      if (kbase + ATT_BN > p.N) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (kbase + i >= p.N) s[i] = -INFINITY;
-      }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-      for (int i = 4; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, s[i]); mx1 = fmaxf(mx1, s[i + 1]);
-        mx2 = fmaxf(mx2, s[i + 2]); mx3 = fmaxf(mx3, s[i + 3]);
-      }
-      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-      const float alpha = fast_exp2((m - m_new) * LOG2E);  // 0 on the first tile (m = -inf)
-      if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
-        // rescale the running O by alpha (per row)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
-          tmem_ld_x32(lane_base + O_COL + uint32_t(c * 32), r);
-          tmem_ld_wait();
+          tmem_ld_x32(s_addr + uint32_t(c * 32), r);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_x32(lane_base + O_COL + uint32_t(c * 32), r);
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
         }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[t]);                  // the tensor pipe may overwrite S_t with the next scores
+        const int kbase = j * ATT_BN;
+        if (kbase + ATT_BN > p.N) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (kbase + i >= p.N) s[i] = -INFINITY;
+        }
+        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
+#pragma unroll
+        for (int i = 8; i < 128; i += 8) {
+          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1])); mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+          mx2 = fmaxf(mx2, fmaxf(s[i + 4], s[i + 5])); mx3 = fmaxf(mx3, fmaxf(s[i + 6], s[i + 7]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j == 0) {
+          m = mx;                                  // first PV overwrites O (accumulate = 0)
+        } else {
+          // PV_t(j-1) must have retired before P_t is overwritten or O_t is rescaled
+          mbar_wait(&pv_done[t], (sc - 1) & 1);
+          tc_fence_after();
+          const bool grow = (mx - m) * LOG2E > RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float m_new = grow ? mx : m;
+            const float alpha = fast_exp2((m - m_new) * LOG2E);   // 1 for the rows that keep their max
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld_x32(o_addr + uint32_t(c * 32), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_x32(o_addr + uint32_t(c * 32), r);
+            }
+            l *= alpha;
+            m = m_new;
+          }
+        }
+        const float2 nmb = make_float2(-m * LOG2E, -m * LOG2E);
+        const float2 l2e = make_float2(LOG2E, LOG2E);
+        float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 x = ffma2(make_float2(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), l2e, nmb);
+            const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            if (i & 1) sum23 = fadd2(sum23, e); else sum01 = fadd2(sum01, e);
+            pk[i] = pack_bf16x2(e.x, e.y);
+          }
+          tmem_st_x16(p_addr + uint32_t(c * 16), pk);
+        }
+        l += (sum01.x + sum01.y) + (sum23.x + sum23.y);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
       }
-      const float mb = m_new * LOG2E;
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+
+      // epilogue: O / l -> bf16 -> out[b*N + q, h*64 + d]
+      mbar_wait(&pv_done[t], (sc - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const int q = q0 + row;
+      __nv_bfloat16* o = p.out + (size_t(b) * p.N + q) * p.D + h * ATT_DH;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t pk[32];
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_x32(o_addr + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        if (q < p.N) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e0 = fast_exp2(fmaf(s[c * 64 + 2 * i], LOG2E, -mb));
-          const float e1 = fast_exp2(fmaf(s[c * 64 + 2 * i + 1], LOG2E, -mb));
-          if (i & 1) { sum2 += e0; sum3 += e1; } else { sum0 += e0; sum1 += e1; }
-          pk[i] = pack_bf16x2(e0, e1);
+          for (int i = 0; i < 32; i += 8) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(o + c * 32 + i) = v;
+          }
         }
-        tmem_st_x32(lane_base + S_COL + uint32_t(c * 32), pk);
       }
-      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
-      m = m_new;
-      tmem_st_wait();
+      // O_t is free again once every thread's tcgen05.ld has completed (wait::ld above); the next
+      // item's first PV_t is ordered after this warpgroup's next p_full arrival.
       tc_fence_before();
-      mbar_arrive(p_full);
-    }
-
-    // epilogue: O / l -> bf16 -> out[b*N + q, h*64 + d]
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const int q = q0 + row;
-    __nv_bfloat16* o = p.out + (size_t(b) * p.N + q) * p.D + h * ATT_DH;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld_x32(lane_base + O_COL + uint32_t(c * 32), r);
-      tmem_ld_wait();
-      if (q < p.N) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-          v.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-          v.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-          v.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(o + c * 32 + i) = v;
-        }
-      }
     }
   }
 

@@ -95,7 +95,7 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 // -----------------------------------------------------------------------------------------
 constexpr int kGemmBN = 128;
 constexpr int kGemmStages = 3;
-constexpr int kAttnStages = 2;
+constexpr int kAttnStages = 4;
 
 template <int EPI>
 cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, cudaStream_t s) {
@@ -125,7 +125,7 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, con
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_attention(const CUtensorMap& qkv, const AttnParams& p, cudaStream_t s) {
+cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
   auto kern = attn_fwd_kernel<kAttnStages>;
   constexpr size_t smem = attn_smem_bytes<kAttnStages>();
   static bool attr[64] = {};
@@ -136,7 +136,9 @@ cudaError_t launch_attention(const CUtensorMap& qkv, const AttnParams& p, cudaSt
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  dim3 grid((p.N + ATT_BM - 1) / ATT_BM, p.H, p.B);
+  p.qpairs = (p.N + 2 * ATT_BM - 1) / (2 * ATT_BM);
+  p.num_items = p.B * p.H * p.qpairs;
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
   kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
   return cudaGetLastError();
 }
@@ -627,7 +629,7 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
       AttnParams p{};
       p.B = batch; p.H = H; p.N = h->Ntok; p.D = D; p.out = h->abuf;
       LaunchScope ls(h, K_ATTN, s);
-      DSG_CUDA(h, launch_attention(h->tm_qkv3d, p, s)); ++n;
+      DSG_CUDA(h, launch_attention(h->tm_qkv3d, p, h->num_sms, s)); ++n;
     }
     {
       GemmParams p{};
@@ -761,7 +763,10 @@ int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* 
   if (!make_tmap_qkv(&tq, qkv, B, N, uint64_t(3) * H * 64)) return -2;
   AttnParams p{};
   p.B = B; p.H = H; p.N = N; p.D = H * 64; p.out = static_cast<__nv_bfloat16*>(out);
-  return launch_attention(tq, p, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return launch_attention(tq, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,

@@ -290,7 +290,9 @@ class DINOSeg(nn.Module):
         need = lib.dinoseg_workspace_bytes(self._handle, batch)
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = None
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            raw = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 1024        # the library wants a 1024-byte aligned scratch
+            self._workspace = raw[off:off + need]
         return self._workspace
 
     # -------------------------------------------------------------------------------------

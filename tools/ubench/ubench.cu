@@ -1,0 +1,143 @@
+// Micro-benchmarks that decide the attention-kernel design on B200 (sm_100a):
+//   per-SM throughput of MUFU.EX2 in f32 / f16x2 / bf16x2 form, the pack conversions, FFMA,
+//   and tcgen05.ld.  One block per SM, clock64() inside the kernel -> ops per clock per SM.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/ubench tools/ubench/ubench.cu
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#include <algorithm>
+
+#define ITERS 2048
+#define ILP 8
+
+template <int MODE>
+__global__ void mufu_kernel(float* out, long long* cycles, float seed) {
+  float f[ILP];
+  uint32_t u[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) { f[i] = seed * (threadIdx.x + i) * 1e-3f - 1.0f; u[i] = 0x3c003800u + threadIdx.x + i; }
+  __syncthreads();
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      if (MODE == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+      if (MODE == 1) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+      if (MODE == 2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u[i]));
+      if (MODE == 3) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(seed), "f"(f[(i + 1) % ILP]));
+      if (MODE == 4) asm volatile("fma.rn.f32 %0, %0, 0f3F8147AE, 0f3DCCCCCD;" : "+f"(f[i]));
+      if (MODE == 5) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(f[i]), "f"(f[(i + 1) % ILP]));
+      if (MODE == 6) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(f[i]), "f"(f[(i + 1) % ILP]));
+      if (MODE == 7) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(seed));
+      if (MODE == 8) asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(f[(i + 1) % ILP]));
+      if (MODE == 9) asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(u[i]) : "r"(u[(i + 1) % ILP]));
+      if (MODE == 10) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) % ILP]));
+      if (MODE == 11) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(*reinterpret_cast<unsigned long long*>(&f[i & ~1])) : "l"(*reinterpret_cast<unsigned long long*>(&f[(i + 2) % ILP & ~1])));
+    }
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += f[i] + __uint_as_float(u[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// tcgen05.ld throughput: W warps (W multiple of 4) each repeatedly load 32 lanes x 32 columns
+__global__ void tmem_ld_kernel(float* out, long long* cycles, int reps, int x64) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t r[32];
+  float acc = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < reps; ++it) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+            "=r"(r[30]), "=r"(r[31])
+          : "r"(base + (uint32_t)(c * 32 + (it & 1) * 128))
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += __uint_as_float(r[it & 31]);
+    }
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(slot) : "memory");
+}
+
+template <int MODE>
+void run(const char* name, int warps, double elems_per_op) {
+  int nsm = 148;
+  float* out; long long* cyc;
+  cudaMalloc(&out, sizeof(float) * nsm * warps * 32);
+  cudaMalloc(&cyc, sizeof(long long) * nsm);
+  mufu_kernel<MODE><<<nsm, warps * 32>>>(out, cyc, 0.37f);
+  cudaDeviceSynchronize();
+  mufu_kernel<MODE><<<nsm, warps * 32>>>(out, cyc, 0.37f);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> h(nsm);
+  cudaMemcpy(h.data(), cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost);
+  std::sort(h.begin(), h.end());
+  double med = double(h[nsm / 2]);
+  double ops = double(warps) * 32 * ITERS * ILP;
+  printf("%-28s warps=%2d  %8.2f inst-lanes/clk/SM  %8.2f elems/clk/SM  (%s)\n", name, warps, ops / med,
+         ops * elems_per_op / med, cudaGetErrorString(e));
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  for (int w : {4, 8, 16}) {
+    run<0>("ex2.approx.ftz.f32", w, 1);
+    run<1>("ex2.approx.f16x2", w, 2);
+    run<2>("ex2.approx.ftz.bf16x2", w, 2);
+    run<3>("fma.f32 (3 reg)", w, 1);
+    run<4>("fma.f32 (imm)", w, 1);
+    run<5>("cvt.rn.bf16x2.f32", w, 2);
+    run<6>("cvt.rn.f16x2.f32", w, 2);
+    run<7>("add.f32", w, 1);
+    run<8>("max.f32", w, 1);
+    run<9>("fma.f16x2", w, 2);
+    run<10>("add.f16x2", w, 2);
+    run<11>("fma.f32x2", w, 2);
+  }
+  for (int w : {4, 8}) {
+    int nsm = 148, reps = 2000;
+    float* out; long long* cyc;
+    cudaMalloc(&out, sizeof(float) * nsm * w * 32);
+    cudaMalloc(&cyc, sizeof(long long) * nsm);
+    tmem_ld_kernel<<<nsm, w * 32>>>(out, cyc, reps, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(nsm);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost);
+    std::sort(h.begin(), h.end());
+    double bytes = double(w) * reps * 4 * 4096.0;
+    printf("tcgen05.ld 32x32b.x32 (ld+wait serial) warps=%d: %.1f B/clk/SM, %.1f clk per x32 load per warp (%s)\n", w,
+           bytes / double(h[nsm / 2]), double(h[nsm / 2]) / (reps * 4.0), cudaGetErrorString(e));
+    cudaFree(out); cudaFree(cyc);
+  }
+  return 0;
+}
