@@ -77,6 +77,31 @@ bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// generic 3-D view {cols, rows, batches} of a row-major buffer (row pitch ld elements, batch pitch
+// rows*ld unless given); box {box_cols, box_rows, 1}, SWIZZLE_128B (box_cols * elem size must be 128 B)
+bool make_tmap_3d(CUtensorMap* m, const void* ptr, bool f32, uint64_t cols, uint64_t rows, uint64_t batches,
+                  uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  const uint64_t es_bytes = f32 ? 4 : 2;
+  cuuint64_t dims[3] = {cols, rows, batches};
+  cuuint64_t strides[2] = {ld * es_bytes, rows * ld * es_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr),
+             dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// A operand of the GEMM: bf16 {K, rows, batches}, box {64, 128, 1}
+bool make_tmap_gemm_a(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t batches, uint64_t K) {
+  return make_tmap_3d(m, ptr, false, K, rows, batches, K, 64, GEMM_BM);
+}
+// output / addend of the GEMM: {N, rows, batches} with row pitch ld; box = one staging chunk (128 B x 128 rows)
+bool make_tmap_gemm_out(CUtensorMap* m, const void* ptr, bool f32, uint64_t N, uint64_t rows, uint64_t batches,
+                        uint64_t ld) {
+  return make_tmap_3d(m, ptr, f32, N, rows, batches, ld, f32 ? 32 : 64, GEMM_BM);
+}
+
 // qkv [B, N, ld] bf16 viewed as {ld, N, B}; box {64, 128, 1}: rows >= N of a frame read as zeros
 bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint64_t ld) {
   PFN_encodeTiled enc = get_encode();
@@ -93,14 +118,13 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 // -----------------------------------------------------------------------------------------
 // kernel launchers
 // -----------------------------------------------------------------------------------------
-constexpr int kGemmBN = 128;
-constexpr int kGemmStages = 3;
 constexpr int kAttnStages = 4;
 
 template <int EPI>
-cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, cudaStream_t s) {
-  auto kern = gemm_bf16_tn_kernel<kGemmBN, EPI, kGemmStages>;
-  constexpr size_t smem = gemm_smem_bytes<kGemmBN, kGemmStages>();
+cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
+                          const GemmParams& p, int num_sms, cudaStream_t s) {
+  auto kern = gemm_bf16_tn_kernel<EPI>;
+  constexpr size_t smem = gemm_smem_bytes(EPI);
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -109,18 +133,23 @@ cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const Gemm
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  dim3 grid((p.N + kGemmBN - 1) / kGemmBN, (p.M + GEMM_BM - 1) / GEMM_BM);
-  kern<<<grid, GEMM_THREADS, smem, s>>>(a, w, p);
+  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
+  const int m_tiles = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM * p.batches;
+  const long long total = (long long)n_tiles * m_tiles;
+  if (total <= 0 || total > INT32_MAX || p.K % GEMM_BK != 0) return cudaErrorInvalidValue;
+  const int grid = total < num_sms ? int(total) : num_sms;   // persistent: one CTA per SM
+  kern<<<grid, GEMM_THREADS, smem, s>>>(a, w, out, add, p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, cudaStream_t s) {
+cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out,
+                        const CUtensorMap& add, const GemmParams& p, int num_sms, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_gemm_t<EPI_BF16>(a, w, p, s);
-    case EPI_GELU_BF16: return launch_gemm_t<EPI_GELU_BF16>(a, w, p, s);
-    case EPI_RESID_F32: return launch_gemm_t<EPI_RESID_F32>(a, w, p, s);
-    case EPI_PATCH_F32: return launch_gemm_t<EPI_PATCH_F32>(a, w, p, s);
-    case EPI_RELU_F32: return launch_gemm_t<EPI_RELU_F32>(a, w, p, s);
+    case EPI_BF16: return launch_gemm_t<EPI_BF16>(a, w, out, add, p, num_sms, s);
+    case EPI_GELU_BF16: return launch_gemm_t<EPI_GELU_BF16>(a, w, out, add, p, num_sms, s);
+    case EPI_RESID_F32: return launch_gemm_t<EPI_RESID_F32>(a, w, out, add, p, num_sms, s);
+    case EPI_PATCH_F32: return launch_gemm_t<EPI_PATCH_F32>(a, w, out, add, p, num_sms, s);
+    case EPI_RELU_F32: return launch_gemm_t<EPI_RELU_F32>(a, w, out, add, p, num_sms, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -233,7 +262,8 @@ struct dinoseg {
   __nv_bfloat16* qkv = nullptr;
   __nv_bfloat16* hid = nullptr;
   uint8_t* lowres_ws = nullptr;
-  CUtensorMap tm_im2col, tm_abuf, tm_hid, tm_qkv3d;
+  CUtensorMap tm_im2col, tm_abuf, tm_hid, tm_qkv3d;           // GEMM A operands / attention input
+  CUtensorMap tm_x_out, tm_x_patch, tm_pos_add, tm_qkv_out, tm_hid_out, tm_h1_out, tm_abuf_out;  // GEMM outputs / addends
 
   int debug_stop = 0;
   int launches = 0;
@@ -309,10 +339,17 @@ int bind_workspace(dinoseg* h, void* ws, size_t ws_bytes, int batch) {
   const uint64_t M = uint64_t(batch) * h->Ntok;
   const uint64_t D = h->cfg.embed_dim;
   bool ok = true;
-  ok &= make_tmap_2d(&h->tm_im2col, h->hid, uint64_t(batch) * h->P, 192, 192, GEMM_BM);
-  ok &= make_tmap_2d(&h->tm_abuf, h->abuf, M, D, D, GEMM_BM);
-  ok &= make_tmap_2d(&h->tm_hid, h->hid, M, h->cfg.mlp_hidden, h->cfg.mlp_hidden, GEMM_BM);
+  const uint64_t HID = h->cfg.mlp_hidden, H1 = h->cfg.head_h1;
+  ok &= make_tmap_gemm_a(&h->tm_im2col, h->hid, h->P, batch, 192);      // per frame: tiles never straddle frames
+  ok &= make_tmap_gemm_a(&h->tm_abuf, h->abuf, M, 1, D);
+  ok &= make_tmap_gemm_a(&h->tm_hid, h->hid, M, 1, HID);
   ok &= make_tmap_qkv(&h->tm_qkv3d, h->qkv, batch, h->Ntok, 3 * D);
+  ok &= make_tmap_gemm_out(&h->tm_x_out, h->x, true, D, M, 1, D);
+  ok &= make_tmap_gemm_out(&h->tm_x_patch, h->x, true, D, h->Ntok, batch, D);
+  ok &= make_tmap_gemm_out(&h->tm_pos_add, h->pos, true, D, h->Ntok, 1, D);
+  ok &= make_tmap_gemm_out(&h->tm_qkv_out, h->qkv, false, 3 * D, M, 1, 3 * D);
+  ok &= make_tmap_gemm_out(&h->tm_hid_out, h->hid, false, HID, M, 1, HID);
+  ok &= make_tmap_gemm_out(&h->tm_h1_out, h->hid, true, H1, M, 1, H1);
   if (!ok) DSG_FAIL(h, "cuTensorMapEncodeTiled failed for the workspace tensor maps");
   h->ws_ptr = ws;
   h->ws_batch = batch;
@@ -427,15 +464,15 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     add_slot(h, pre + "mlp.fc1.weight", 1, b.fc1_w, {HID, D}); add_slot(h, pre + "mlp.fc1.bias", 0, b.fc1_b, {HID});
     add_slot(h, pre + "mlp.fc2.weight", 1, b.fc2_w, {D, HID}); add_slot(h, pre + "mlp.fc2.bias", 0, b.fc2_b, {D});
     bool ok = true;
-    ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, kGemmBN);
-    ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, kGemmBN);
-    ok &= make_tmap_2d(&b.tm_fc1, b.fc1_w, HID, D, D, kGemmBN);
-    ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, kGemmBN);
+    ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, GEMM_BN);
+    ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, GEMM_BN);
+    ok &= make_tmap_2d(&b.tm_fc1, b.fc1_w, HID, D, D, GEMM_BN);
+    ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, GEMM_BN);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed for block weights"; rc = -1; }
   }
   if (rc == 0) {
-    bool ok = make_tmap_2d(&h->tm_pe, h->pe_w, D, 192, 192, kGemmBN);
-    ok &= make_tmap_2d(&h->tm_h1, h->h1_w, H1, D, D, kGemmBN);
+    bool ok = make_tmap_2d(&h->tm_pe, h->pe_w, D, 192, 192, GEMM_BN);
+    ok &= make_tmap_2d(&h->tm_h1, h->h1_w, H1, D, D, GEMM_BN);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed for patch/head weights"; rc = -1; }
   }
   if (rc != 0) {
@@ -598,6 +635,13 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
   if (!h->profile) h->ev_used = 0;
 
   // ---- prepare_tokens (vision_transformer.py:224-235) ----
+  const int sms = h->num_sms;
+  auto gp = [&](int N, int K, const float* bias) {
+    GemmParams p{};
+    p.N = N; p.K = K; p.rows_per_batch = M; p.batches = 1; p.row_off = 0; p.add_batched = 0; p.bias = bias;
+    p.col_scale = 1.f; p.scale_cols = 0;
+    return p;
+  };
   { LaunchScope ls(h, K_IM2COL, s); DSG_CUDA(h, launch_im2col(frames, h->hid, batch, h->g, s)); ++n; }
   {
     LaunchScope ls(h, K_CLS, s);
@@ -605,11 +649,10 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
     DSG_CUDA(h, cudaGetLastError()); ++n;
   }
   {
-    GemmParams p{};
-    p.M = batch * h->P; p.N = D; p.K = 192; p.bias = h->pe_b; p.out = h->x; p.ldo = D;
-    p.pos = h->pos; p.P = h->P; p.Ntok = h->Ntok;
+    GemmParams p = gp(D, 192, h->pe_b);
+    p.rows_per_batch = h->P; p.batches = batch; p.row_off = 1;   // out row = b*Ntok + 1 + t, + pos[1 + t]
     LaunchScope ls(h, K_GEMM_PATCH, s);
-    DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, h->tm_im2col, h->tm_pe, p, s)); ++n;
+    DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, h->tm_im2col, h->tm_pe, h->tm_x_patch, h->tm_pos_add, p, sms, s)); ++n;
   }
   if (stop == 1) { h->launches = n; return 0; }
 
@@ -618,11 +661,10 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
     BlockW& b = h->blocks[i];
     { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, b.ln1_g, b.ln1_b, h->abuf, M, D, eps, s)); ++n; }
     {
-      GemmParams p{};
-      p.M = M; p.N = 3 * D; p.K = D; p.bias = b.qkv_b; p.out = h->qkv; p.ldo = 3 * D;
+      GemmParams p = gp(3 * D, D, b.qkv_b);
       p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
       LaunchScope ls(h, K_GEMM_QKV, s);
-      DSG_CUDA(h, launch_gemm(EPI_BF16, h->tm_abuf, b.tm_qkv, p, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_BF16, h->tm_abuf, b.tm_qkv, h->tm_qkv_out, h->tm_qkv_out, p, sms, s)); ++n;
     }
     if (stop == 2 + 3 * i) { h->launches = n; return 0; }
     {
@@ -632,24 +674,21 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
       DSG_CUDA(h, launch_attention(h->tm_qkv3d, p, h->num_sms, s)); ++n;
     }
     {
-      GemmParams p{};
-      p.M = M; p.N = D; p.K = D; p.bias = b.proj_b; p.out = h->x; p.ldo = D;
+      GemmParams p = gp(D, D, b.proj_b);
       LaunchScope ls(h, K_GEMM_PROJ, s);
-      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_abuf, b.tm_proj, p, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_abuf, b.tm_proj, h->tm_x_out, h->tm_x_out, p, sms, s)); ++n;
     }
     if (stop == 3 + 3 * i) { h->launches = n; return 0; }
     { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, b.ln2_g, b.ln2_b, h->abuf, M, D, eps, s)); ++n; }
     {
-      GemmParams p{};
-      p.M = M; p.N = HID; p.K = D; p.bias = b.fc1_b; p.out = h->hid; p.ldo = HID;
+      GemmParams p = gp(HID, D, b.fc1_b);
       LaunchScope ls(h, K_GEMM_FC1, s);
-      DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, h->tm_abuf, b.tm_fc1, p, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, h->tm_abuf, b.tm_fc1, h->tm_hid_out, h->tm_hid_out, p, sms, s)); ++n;
     }
     {
-      GemmParams p{};
-      p.M = M; p.N = D; p.K = HID; p.bias = b.fc2_b; p.out = h->x; p.ldo = D;
+      GemmParams p = gp(D, HID, b.fc2_b);
       LaunchScope ls(h, K_GEMM_FC2, s);
-      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_hid, b.tm_fc2, p, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_hid, b.tm_fc2, h->tm_x_out, h->tm_x_out, p, sms, s)); ++n;
     }
     if (stop == 4 + 3 * i) { h->launches = n; return 0; }
   }
@@ -658,10 +697,9 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
   { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, h->norm_g, h->norm_b, h->abuf, M, D, eps, s)); ++n; }
   float* h1 = reinterpret_cast<float*>(h->hid);
   {
-    GemmParams p{};
-    p.M = M; p.N = h->cfg.head_h1; p.K = D; p.bias = h->h1_b; p.out = h1; p.ldo = h->cfg.head_h1;
+    GemmParams p = gp(h->cfg.head_h1, D, h->h1_b);
     LaunchScope ls(h, K_GEMM_HEAD, s);
-    DSG_CUDA(h, launch_gemm(EPI_RELU_F32, h->tm_abuf, h->tm_h1, p, s)); ++n;
+    DSG_CUDA(h, launch_gemm(EPI_RELU_F32, h->tm_abuf, h->tm_h1, h->tm_h1_out, h->tm_h1_out, p, sms, s)); ++n;
   }
   uint8_t* lr = lowres ? lowres : h->lowres_ws;
   {
@@ -747,14 +785,32 @@ int64_t dinoseg_copy_buffer(dinoseg_t* h, const char* name, void* dst, size_t ds
 // ---- kernel-level entry points ------------------------------------------------------------
 int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo, int epi,
                     float col_scale, int scale_cols, const float* pos, int P, int Ntok, void* stream) {
-  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0) return -1;
-  if ((epi == EPI_BF16 || epi == EPI_GELU_BF16) ? (N % 8 != 0) : (N % 4 != 0)) return -1;
-  CUtensorMap ta, tw;
-  if (!make_tmap_2d(&ta, A, M, K, K, GEMM_BM) || !make_tmap_2d(&tw, W, N, K, K, kGemmBN)) return -2;
+  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0 || (K % GEMM_BK) != 0 || epi < 0 || epi > EPI_RELU_F32) return -1;
+  const bool f32 = gemm_out_is_f32(epi);
+  if (f32 ? (N % 4 != 0) : (N % 8 != 0)) return -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap ta, tw, to, tadd;
   GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = ldo;
-  p.col_scale = col_scale; p.scale_cols = scale_cols; p.pos = pos; p.P = P; p.Ntok = Ntok;
-  return launch_gemm(epi, ta, tw, p, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+  p.N = N; p.K = K; p.bias = bias; p.col_scale = col_scale; p.scale_cols = scale_cols;
+  bool ok = make_tmap_2d(&tw, W, N, K, K, GEMM_BN);
+  if (epi == EPI_PATCH_F32) {
+    // A [B*P, K] -> out [B*Ntok, N]: row b*Ntok + 1 + t = acc + bias + pos[1 + t]
+    if (!pos || P <= 0 || Ntok != P + 1 || M % P != 0) return -1;
+    const int B = M / P;
+    p.rows_per_batch = P; p.batches = B; p.row_off = 1; p.add_batched = 0;
+    ok &= make_tmap_gemm_a(&ta, A, P, B, K);
+    ok &= make_tmap_gemm_out(&to, out, true, N, Ntok, B, ldo);
+    ok &= make_tmap_gemm_out(&tadd, pos, true, N, Ntok, 1, N);
+  } else {
+    p.rows_per_batch = M; p.batches = 1; p.row_off = 0; p.add_batched = 0;
+    ok &= make_tmap_gemm_a(&ta, A, M, 1, K);
+    ok &= make_tmap_gemm_out(&to, out, f32, N, M, 1, ldo);
+    tadd = to;
+  }
+  if (!ok) return -2;
+  return launch_gemm(epi, ta, tw, to, tadd, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {

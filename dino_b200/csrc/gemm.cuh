@@ -6,10 +6,18 @@
 //   patch-embed (reference vision_transformer.py:153-157 as an im2col GEMM), qkv (:75,:82),
 //   proj (:77,:105), fc1/GELU (:54-55,:60-61), fc2 (:56,:63), head layer_1 (pl_torch_modules.py:113,118).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0      : TMA producer  (A tile 128x64, W tile BNx64 per k-block, SWIZZLE_128B, STAGES-deep ring)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulator 128 lanes x BN fp32 columns)
-//   warps 2..5  : epilogue: tcgen05.ld (32x32b: one accumulator row per thread) -> bias/activation -> global
+// Persistent, warp-specialised (192 threads, 1 CTA per SM, tile = 128 x 192, n-tiles fastest so the
+// CTAs that run concurrently share their A rows through L2):
+//   warp 0      : TMA producer  (A tile 128x64, W tile 192x64 per k-block, SWIZZLE_128B, ring of STAGES)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulator stages
+//                 (2 x 192 fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2..5  : epilogue: tcgen05.ld (one accumulator row per thread) -> bias / activation / addend
+//                 -> swizzled shared-memory staging -> TMA store (fully coalesced, tails clipped by
+//                 the tensor map).  Addends (residual stream, positional table) are TMA-loaded into
+//                 the same staging buffers two chunks ahead.
+// All global tensors are described by 3-D tensor maps {cols, rows_per_batch, batches}; plain
+// matrices use batches = 1.  The patch-embed GEMM uses batches = frames so that a tile never
+// straddles two frames and its output can skip each frame's cls row (row offset 1).
 #pragma once
 #include "ptx.cuh"
 
@@ -18,65 +26,104 @@ namespace dsg {
 enum : int {
   EPI_BF16 = 0,       // out bf16 = (acc + bias) * (col < scale_cols ? col_scale : 1)
   EPI_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
-  EPI_RESID_F32 = 2,  // out f32 += acc + bias        (in-place residual add)
-  EPI_PATCH_F32 = 3,  // out f32[(r/P)*Ntok + 1 + r%P] = acc + bias + pos[1 + r%P]
+  EPI_RESID_F32 = 2,  // out f32 = addend + acc + bias      (addend = out: in-place residual add)
+  EPI_PATCH_F32 = 3,  // out f32[b, 1 + t] = acc + bias + pos[1 + t]   (addend = positional table)
   EPI_RELU_F32 = 4,   // out f32 = relu(acc + bias)
 };
 
 struct GemmParams {
-  int M, N, K;
-  const float* bias;  // [N] (may be null)
-  void* out;
-  int ldo;  // leading dimension of out, in elements
+  int N, K;             // output columns, reduction length (K % 64 == 0)
+  int rows_per_batch;   // rows of A / out per batch
+  int batches;
+  int row_off;          // output (and addend) row offset inside a batch (1 for the patch embed: cls row)
+  int add_batched;      // 1: addend indexed by batch, 0: addend shared by all batches
+  const float* bias;    // [N] (may be null)
   float col_scale;
   int scale_cols;
-  const float* pos;  // EPI_PATCH_F32: [Ntok, N] positional table (row 0 = cls)
-  int P, Ntok;
 };
 
 constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 192;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;   // 24 KB
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
+constexpr int GEMM_STG_BYTES = 128 * 128;             // one staging buffer: 128 rows x 128 bytes
 
-template <int BN, int STAGES>
-constexpr size_t gemm_smem_bytes() {
-  return size_t(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+__host__ __device__ constexpr bool gemm_out_is_f32(int epi) { return epi >= EPI_RESID_F32; }
+__host__ __device__ constexpr bool gemm_has_addend(int epi) { return epi == EPI_RESID_F32 || epi == EPI_PATCH_F32; }
+__host__ __device__ constexpr int gemm_stages(int epi) { return gemm_out_is_f32(epi) ? 3 : 4; }
+__host__ __device__ constexpr int gemm_nbuf(int epi) { return gemm_out_is_f32(epi) ? 4 : 2; }
+__host__ __device__ constexpr size_t gemm_smem_bytes(int epi) {
+  return size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES + size_t(gemm_nbuf(epi)) * GEMM_STG_BYTES + 1024 /*align*/ + 256;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU with the exact-erf definition (nn.GELU() default, reference vision_transformer.py:50):
+//   gelu(x) = x * Phi(x),  Phi(-|x|) = 0.5 * erfc(|x|/sqrt2) = 0.5 * 2^-q(|x|)
+// q = -log2(erfc(|x|/sqrt2)) is smooth; a degree-6 polynomial on [0, 4.95] (Chebyshev fit) gives
+// |gelu - exact| <= 3e-6 in fp32 (tools/fit_gelu.py), 1000x below the bf16 rounding of the result,
+// for 6 FMA + 1 MUFU.EX2 instead of erff()'s ~30 instructions.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fminf(fabsf(x), 4.949747468f);
+  float q = -3.0103274184511974e-05f;
+  q = fmaf(q, ax, 0.0007183064590208232f);
+  q = fmaf(q, ax, -0.007799314800649881f);
+  q = fmaf(q, ax, 0.05274621397256851f);
+  q = fmaf(q, ax, 0.45945441722869873f);
+  q = fmaf(q, ax, 1.150948166847229f);
+  q = fmaf(q, ax, 1.0440264304634184e-05f);
+  const float w = 0.5f * fast_exp2(-q);          // Phi(-|x|)
+  return x >= 0.f ? fmaf(-x, w, x) : x * w;
+}
 
-template <int BN, int EPI, int STAGES>
+template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
                     const GemmParams p) {
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
-  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  constexpr int B_BYTES = BN * GEMM_BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr bool OUT_F32 = gemm_out_is_f32(EPI);
+  constexpr bool HAS_ADD = gemm_has_addend(EPI);
+  constexpr int STAGES = gemm_stages(EPI);
+  constexpr int NBUF = gemm_nbuf(EPI);
+  constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 bytes per row)
+  constexpr int NCH = GEMM_BN / CH;
+  constexpr int PD = HAS_ADD ? 2 : 0;            // addend prefetch distance in chunks
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t ACC_STRIDE = 256;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * STAGE_BYTES);
+  uint8_t* stg = smem + size_t(STAGES) * GEMM_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + size_t(NBUF) * GEMM_STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;       // 2
+  uint64_t* acc_empty = acc_full + 2;            // 2 (4 arrivals: one per epilogue warp)
+  uint64_t* add_bar = acc_empty + 2;             // NBUF
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * GEMM_BM;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = p.K / GEMM_BK;
+  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
+  const int m_tiles_pb = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM;
+  const int total_tiles = n_tiles * m_tiles_pb * p.batches;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
+    if (HAS_ADD) tma_prefetch_desc(&tmAdd);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    for (int s = 0; s < NBUF; ++s) mbar_init(&add_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -87,113 +134,166 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
-        tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
-        tma_load_2d(sa + A_BYTES, &tmW, &full_bar[s], kb * GEMM_BK, n0);
+      uint32_t kc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        const int mt = tile / n_tiles;
+        const int bt = mt / m_tiles_pb;
+        const int r0 = (mt - bt * m_tiles_pb) * GEMM_BM;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], GEMM_STAGE_BYTES);
+          uint8_t* sa = smem + size_t(s) * GEMM_STAGE_BYTES;
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, r0, bt);
+          tma_load_2d(sa + GEMM_A_BYTES, &tmW, &full_bar[s], kb * GEMM_BK, nt * GEMM_BN);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN, 0);
+      uint32_t kc = 0;
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int as = ti & 1;
+        mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + size_t(s) * STAGE_BYTES);
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+        const uint32_t d_tmem = tmem_base + uint32_t(as) * ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(s) * GEMM_STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + GEMM_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >>4 -> +2)
-          umma_ss(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >>4 -> +2)
+            umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[s]);
         }
-        tc_commit(&empty_bar[s]);
+        tc_commit(&acc_full[as]);
       }
-      tc_commit(acc_bar);
     }
   } else {
     // ---------------- epilogue: thread <-> accumulator row ----------------
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const int grow = m0 + row;
-    const bool row_ok = grow < p.M;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
+    const bool leader = threadIdx.x == 64;
+    const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
+    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+    const int total_chunks = my_tiles * NCH;
 
-    size_t out_row = size_t(grow);
-    const float* pos_row = nullptr;
-    if constexpr (EPI == EPI_PATCH_F32) {
-      const int b = grow / p.P;
-      const int t = grow - b * p.P;
-      out_row = size_t(b) * p.Ntok + 1 + t;
-      pos_row = p.pos + size_t(1 + t) * p.N;
+    // coordinates of this CTA's q-th chunk (q = tile_iter * NCH + c)
+    auto chunk_coords = [&](int q, int& col0, int& r0, int& bt) {
+      const int tile = int(blockIdx.x) + (q / NCH) * int(gridDim.x);
+      const int nt = tile % n_tiles;
+      const int mt = tile / n_tiles;
+      bt = mt / m_tiles_pb;
+      r0 = (mt - bt * m_tiles_pb) * GEMM_BM;
+      col0 = nt * GEMM_BN + (q % NCH) * CH;
+    };
+    auto issue_add = [&](int q) {
+      int col0, r0, bt;
+      chunk_coords(q, col0, r0, bt);
+      const int b = q % NBUF;
+      mbar_expect_tx(&add_bar[b], GEMM_STG_BYTES);
+      tma_load_3d(stg + size_t(b) * GEMM_STG_BYTES, &tmAdd, &add_bar[b], col0, p.row_off + r0, p.add_batched ? bt : 0);
+    };
+    if (HAS_ADD && leader) {
+      for (int q = 0; q < PD && q < total_chunks; ++q) issue_add(q);
     }
 
+    int g = 0;                                     // chunk counter of this CTA
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int as = ti & 1;
+      mbar_wait(&acc_full[as], (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = lane_base + uint32_t(as) * ACC_STRIDE;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
-      tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c * 32), r);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= p.N) continue;
-      float v[32];
+      for (int c = 0; c < NCH; ++c, ++g) {
+        int col0, r0, bt;
+        chunk_coords(g, col0, r0, bt);
+        const int b = g % NBUF;
+        uint8_t* sb = stg + size_t(b) * GEMM_STG_BYTES;
+        // accumulator chunk -> registers
+        float v[CH];
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      if (p.bias != nullptr) {
+        for (int h = 0; h < CH / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld_x32(acc + uint32_t(c * CH + h * 32), r);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (col0 + i < p.N) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          for (int i = 0; i < 32; ++i) v[h * 32 + i] = __uint_as_float(r[i]);
+        }
+        tmem_ld_wait();
+        if (c == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);   // the MMA warp may start tile ti+2 in this stage
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < CH; i += 4) {
+            if (col0 + i < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
           }
         }
-      }
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + col0;
+        // staging buffer b: the TMA store that last read it (chunk g - NBUF) must be done, and for
+        // addend epilogues the prefetch of chunk g + PD goes into the buffer of chunk g + PD - NBUF
+        if (leader) {
+          tma_store_wait_read<NBUF - PD - 1>();
+          if (HAS_ADD && g + PD < total_chunks) issue_add(g + PD);
+        }
+        if constexpr (HAS_ADD) {
+          mbar_wait(&add_bar[b], (g / NBUF) & 1);
+        } else {
+          named_bar_sync(1, 128);
+        }
+        uint8_t* srow = sb + row * 128;
+        if constexpr (OUT_F32) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          if (col0 + i < p.N) {
+          for (int k = 0; k < 8; ++k) {
+            float4* ptr = reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4));
+            float4 q = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            if constexpr (HAS_ADD) {
+              const float4 a = *ptr;
+              q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+            } else if constexpr (EPI == EPI_RELU_F32) {
+              q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f);
+            }
+            *ptr = q;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
             float w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float x = v[i + j];
+              float x = v[8 * k + j];
               if constexpr (EPI == EPI_GELU_BF16) x = gelu_erf(x);
-              else if (col0 + i + j < p.scale_cols) x *= p.col_scale;
+              else if (col0 + 8 * k + j < p.scale_cols) x *= p.col_scale;
               w[j] = x;
             }
             uint4 q;
             q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
             q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
-            *reinterpret_cast<uint4*>(o + i) = q;
+            *reinterpret_cast<uint4*>(srow + ((k ^ (row & 7)) << 4)) = q;
           }
         }
-      } else {
-        float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + col0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (col0 + i < p.N) {
-            float4 q = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            if constexpr (EPI == EPI_RESID_F32) {
-              const float4 x = *reinterpret_cast<const float4*>(o + i);
-              q.x += x.x; q.y += x.y; q.z += x.z; q.w += x.w;
-            } else if constexpr (EPI == EPI_PATCH_F32) {
-              const float4 x = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + i));
-              q.x += x.x; q.y += x.y; q.z += x.z; q.w += x.w;
-            } else if constexpr (EPI == EPI_RELU_F32) {
-              q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(o + i) = q;
-          }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (leader) {
+          if (col0 < p.N) tma_store_3d(&tmOut, sb, col0, p.row_off + r0, bt);
+          tma_store_commit();
         }
       }
     }
+    if (leader) tma_store_wait<0>();               // all output bytes are globally visible before exit
   }
 
   tc_fence_before();
