@@ -42,7 +42,14 @@ struct AttnParams {
   __nv_bfloat16* out;   // [B*N, D], column = h*64 + d   (reference :104 transpose(1,2).reshape)
   int qpairs;           // ceil(N / 256)
   int num_items;        // B * H * qpairs
+  long long* timing;    // debug (DSG_ATTN_TIMING builds): [grid][2 warpgroups][8] phase cycle totals
 };
+
+#ifdef DSG_ATTN_TIMING
+#define ATT_T(i) do { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } while (0)
+#else
+#define ATT_T(i) do { } while (0)
+#endif
 
 constexpr int ATT_BM = 128;     // queries per tile (two tiles per work item)
 constexpr int ATT_BN = 128;     // keys per tile
@@ -84,11 +91,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint64_t* pv_done = p_full + 2;              // 2: PV_t(j) retired (P_t free again, O_t stable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
@@ -112,7 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
   if (warp < 4) {
     setmaxnreg_dec_80();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
       // ------------------------------ TMA producer ------------------------------
       uint32_t kvc = 0;
       int it = 0;
@@ -135,7 +142,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           tma_load_3d(sk + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.D + h * ATT_DH, j * ATT_BN, b);
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
       // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0);  // K^T: K-major B
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_DH, 1);  // V  : MN-major B
@@ -143,6 +150,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const uint64_t qdesc1 = umma_desc_sw128(smem_u32(sQ + ATT_TILE_BYTES));
       uint32_t kvc = 0, c0 = 0, c1 = 0;   // c_t: key tiles of query tile t processed so far (barrier phases)
       int it = 0;
+#ifdef DSG_ATTN_TIMING
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tprev = clock64();
+#endif
       auto issue_qk = [&](int t, uint32_t kv_counter) {
         const uint32_t sk = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES);
         const uint64_t kdesc = umma_desc_sw128(sk);
@@ -176,28 +187,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           const bool more = j + 1 < num_tiles;
           if (more) {
             // next scores as soon as the softmax warps hold the current ones in registers
+            ATT_T(7);
             mbar_wait(&kv_full[(kvc + 1) % KV_STAGES], ((kvc + 1) / KV_STAGES) & 1);
+            ATT_T(0);
             mbar_wait(&s_empty[0], c0 & 1);
+            ATT_T(1);
             tc_fence_after();
             issue_qk(0, kvc + 1);
+            ATT_T(6);
             if (two) {
               mbar_wait(&s_empty[1], c1 & 1);
+              ATT_T(2);
               tc_fence_after();
               issue_qk(1, kvc + 1);
+              ATT_T(6);
             }
             if (j + 2 == num_tiles) tc_commit(q_empty);  // last reads of Q0/Q1 have been issued
           }
+          ATT_T(7);
           mbar_wait(&p_full[0], c0 & 1); ++c0;
+          ATT_T(3);
           tc_fence_after();
           issue_pv(0, kvc, j != 0);
+          ATT_T(6);
           if (two) {
             mbar_wait(&p_full[1], c1 & 1); ++c1;
+            ATT_T(4);
             tc_fence_after();
             issue_pv(1, kvc, j != 0);
+            ATT_T(6);
           }
           tc_commit(&kv_empty[kvc % KV_STAGES]);      // K(j), V(j) fully consumed once these MMAs retire
         }
       }
+#ifdef DSG_ATTN_TIMING
+      if (p.timing != nullptr)
+        for (int i = 0; i < 8; ++i) p.timing[(size_t(gridDim.x) * 2 + blockIdx.x) * 8 + i] = tacc[i];
+#endif
     }
   } else {
     // ------------------------------ softmax warpgroups ------------------------------
@@ -210,6 +236,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t o_addr = lane_base + O_COL0 + uint32_t(t * 64);
     const uint32_t p_addr = lane_base + P_COL0 + uint32_t(t * 64);
     uint32_t sc = 0;                               // key tiles processed so far by this warpgroup
+#ifdef DSG_ATTN_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#endif
+    if (t == 1) named_bar_arrive(2, 256);          // ping-pong token: warpgroup 0 goes first
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int qp = item % p.qpairs;
@@ -217,12 +248,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const int h = bh % p.H, b = bh / p.H;
       const int q0 = qp * 2 * ATT_BM + t * ATT_BM;
       if (q0 >= p.N) continue;                     // second tile of the last pair may be empty
+      const bool two = qp * 2 * ATT_BM + ATT_BM < p.N;   // both warpgroups work on this item
       float m = 0.f;                               // (stale) running row max of the raw scores
       float l = 0.f;                               // running row sum of exp(s - m)
 
       for (int j = 0; j < num_tiles; ++j, ++sc) {
+        ATT_T(7);
         mbar_wait(&s_full[t], sc & 1);
         tc_fence_after();
+        ATT_T(0);
         float s[128];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -232,6 +266,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
         }
         tmem_ld_wait();
+        ATT_T(1);
         tc_fence_before();
         mbar_arrive(&s_empty[t]);                  // the tensor pipe may overwrite S_t with the next scores
         const int kbase = j * ATT_BN;
@@ -247,12 +282,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           mx2 = fmaxf(mx2, fmaxf(s[i + 4], s[i + 5])); mx3 = fmaxf(mx3, fmaxf(s[i + 6], s[i + 7]));
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        ATT_T(2);
         if (j == 0) {
           m = mx;                                  // first PV overwrites O (accumulate = 0)
         } else {
           // PV_t(j-1) must have retired before P_t is overwritten or O_t is rescaled
           mbar_wait(&pv_done[t], (sc - 1) & 1);
           tc_fence_after();
+          ATT_T(3);
           const bool grow = (mx - m) * LOG2E > RESCALE_THRESHOLD;
           if (__any_sync(0xffffffffu, grow)) {
             const float m_new = grow ? mx : m;
@@ -273,22 +310,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         const float2 nmb = make_float2(-m * LOG2E, -m * LOG2E);
         const float2 l2e = make_float2(LOG2E, LOG2E);
         float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
+        // MUFU ping-pong: the two warpgroups take turns in the exponential phase, so that the loads /
+        // row-max / barrier phases of one always run under the other one's MUFU work
+        if (two) named_bar_sync(2 + t, 256);
+        ATT_T(4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 x = ffma2(make_float2(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), l2e, nmb);
+#ifdef DSG_EXP_NO_MUFU
+            const float2 e = x;
+#else
             const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+#endif
+#ifndef DSG_EXP_NO_SUM
             if (i & 1) sum23 = fadd2(sum23, e); else sum01 = fadd2(sum01, e);
+#else
+            sum01.x = e.x;
+#endif
+#ifndef DSG_EXP_NO_PACK
             pk[i] = pack_bf16x2(e.x, e.y);
+#else
+            pk[i] = __float_as_uint(e.x) ^ __float_as_uint(e.y);
+#endif
           }
+#ifndef DSG_EXP_NO_ST
           tmem_st_x16(p_addr + uint32_t(c * 16), pk);
+#else
+          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u && pk[15] == pk[3]) tmem_st_x16(p_addr + uint32_t(c * 16), pk);
+#endif
         }
+        ATT_T(5);
+        if (two) named_bar_arrive(3 - t, 256);
         l += (sum01.x + sum01.y) + (sum23.x + sum23.y);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[t]);
+        ATT_T(6);
       }
 
       // epilogue: O / l -> bf16 -> out[b*N + q, h*64 + d]
@@ -319,6 +379,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       // item's first PV_t is ordered after this warpgroup's next p_full arrival.
       tc_fence_before();
     }
+#ifdef DSG_ATTN_TIMING
+    if (p.timing != nullptr && (threadIdx.x & 127) == 0) {
+      for (int i = 0; i < 8; ++i) p.timing[(size_t(blockIdx.x) * 2 + t) * 8 + i] = tacc[i];
+    }
+#endif
   }
 
   tc_fence_before();

@@ -154,7 +154,10 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, con
   return cudaErrorInvalidValue;
 }
 
+long long* g_attn_timing = nullptr;   // debug: device buffer for DSG_ATTN_TIMING builds
+
 cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
+  p.timing = g_attn_timing;
   auto kern = attn_fwd_kernel<kAttnStages>;
   constexpr size_t smem = attn_smem_bytes<kAttnStages>();
   static bool attr[64] = {};
@@ -811,6 +814,16 @@ int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, 
   }
   if (!ok) return -2;
   return launch_gemm(epi, ta, tw, to, tadd, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_debug_set_attn_timing(long long* dev_ptr) {
+#ifdef DSG_ATTN_TIMING
+  g_attn_timing = dev_ptr;
+  return 0;
+#else
+  (void)dev_ptr;
+  return -1;   // the library was not built with -DDSG_ATTN_TIMING
+#endif
 }
 
 int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {

@@ -103,14 +103,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* add_bar = acc_empty + 2;             // NBUF
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + NBUF);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role index (the shuffle tells the compiler so) + elect.sync for the single issuing thread:
+  // with a threadIdx-derived predicate every tcgen05.mma / TMA instruction gets wrapped in a divergence
+  // 'waterfall' loop that costs ~100 clk per MMA (measured: tools/ubench/mma_bench.cu)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int num_kb = p.K / GEMM_BK;
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int m_tiles_pb = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM;
   const int total_tiles = n_tiles * m_tiles_pb * p.batches;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmOut);
@@ -133,7 +136,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t kc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_tiles;
@@ -151,7 +154,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN, 0);
       uint32_t kc = 0;
       int ti = 0;

@@ -74,7 +74,9 @@ def init_state_dict(cfg: dict, seed: int = 0, variant: str = "reference_init") -
     for i in range(cfg["n_blocks"]):
         p = f"dino.blocks.{i}."
         ln(p + "norm1")
-        lin(p + "attn.qkv", 3 * D, D, 0.02 if not tl else 0.09)
+        # trained_like: std chosen so that the attention logits have the same spread (std ~3) for
+        # every embed dim (q.k grows with D * std^4)
+        lin(p + "attn.qkv", 3 * D, D, 0.02 if not tl else 0.09 * (384.0 / D) ** 0.5)
         lin(p + "attn.proj", D, D, 0.02 if not tl else 0.04)
         ln(p + "norm2")
         lin(p + "mlp.fc1", HID, D, 0.02 if not tl else 0.05)

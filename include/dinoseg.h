@@ -114,6 +114,9 @@ int dinoseg_op_gemm(const void* A_bf16, const void* W_bf16, const float* bias, v
                     void* stream);
 /* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16 (q pre-scaled) */
 int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int H, void* stream);
+/* Debug builds only (-DDSG_ATTN_TIMING): device buffer [grid][2][8] of int64 receiving the per-phase
+ * cycle totals of the attention kernel's softmax warpgroups; returns -1 in regular builds. */
+int dinoseg_debug_set_attn_timing(long long* dev_ptr);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
                          float eps, void* stream);
 int dinoseg_op_posembed(const float* pos_src, float* out, int G0, int g, int D, void* stream);

@@ -145,9 +145,12 @@ def main():
     hist = survey_anchor(plm)
     with open(os.path.join(OUT, "survey_anchor.json"), "w") as f:
         json.dump({"label_histogram": hist, "expected_in_SURVEY": [80, 2, 956, 93, 344, 42, 5683]}, f)
+    only = set(sys.argv[1:])          # optional: regenerate only the named cases
     for c in CASES:
-        run_case(plm, vt, *c)
-    predict_case(plm, vt)
+        if not only or c[0] in only:
+            run_case(plm, vt, *c)
+    if not only or "predict" in only:
+        predict_case(plm, vt)
 
 
 if __name__ == "__main__":

@@ -47,6 +47,46 @@ __global__ void mufu_kernel(float* out, long long* cycles, float seed) {
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// the softmax inner loop of the attention kernel: per pair FFMA2, 2 x MUFU.EX2, FADD2, F2FP
+__global__ void softmax_body_kernel(float* out, long long* cycles, float seed, int poly_every) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = seed * (threadIdx.x + i) * 1e-3f - 1.0f;
+  unsigned long long sum01 = 0ull, sum23 = 0ull;
+  const float2 l2e2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
+  const float2 nmb2 = make_float2(-seed, -seed);
+  const unsigned long long l2e = *reinterpret_cast<const unsigned long long*>(&l2e2);
+  const unsigned long long nmb = *reinterpret_cast<const unsigned long long*>(&nmb2);
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS / 4; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      unsigned long long x, e;
+      float2 sv = make_float2(v[2 * i], v[2 * i + 1]);
+      asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(*reinterpret_cast<unsigned long long*>(&sv)), "l"(l2e), "l"(nmb));
+      float2 xf = *reinterpret_cast<float2*>(&x);
+      float e0, e1;
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(xf.x));
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(xf.y));
+      float2 ef = make_float2(e0, e1);
+      e = *reinterpret_cast<unsigned long long*>(&ef);
+      if (i & 1) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(sum23) : "l"(e));
+      else asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(sum01) : "l"(e));
+      uint32_t pk;
+      asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(e1), "f"(e0));
+      acc ^= pk;
+      v[2 * i] = e0 - 1.5f;   // keep a loop-carried dependence so nothing is hoisted
+    }
+  }
+  long long t1 = clock64();
+  float2 a = *reinterpret_cast<float2*>(&sum01), b = *reinterpret_cast<float2*>(&sum23);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a.x + a.y + b.x + b.y + __uint_as_float(acc);
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 // tcgen05.ld throughput: W warps (W multiple of 4) each repeatedly load 32 lanes x 32 columns
 __global__ void tmem_ld_kernel(float* out, long long* cycles, int reps, int x64) {
   __shared__ uint32_t slot;
@@ -78,7 +118,7 @@ __global__ void tmem_ld_kernel(float* out, long long* cycles, int reps, int x64)
           : "r"(base + (uint32_t)(c * 32 + (it & 1) * 128))
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc += __uint_as_float(r[it & 31]);
+      acc += __uint_as_float(r[0]) + __uint_as_float(r[31]);
     }
   }
   long long t1 = clock64();
@@ -123,6 +163,23 @@ int main() {
     run<9>("fma.f16x2", w, 2);
     run<10>("add.f16x2", w, 2);
     run<11>("fma.f32x2", w, 2);
+  }
+  for (int w : {4, 8, 12, 16}) {
+    int nsm = 148;
+    float* out; long long* cyc;
+    cudaMalloc(&out, sizeof(float) * nsm * w * 32);
+    cudaMalloc(&cyc, sizeof(long long) * nsm);
+    softmax_body_kernel<<<nsm, w * 32>>>(out, cyc, 0.37f, 0);
+    cudaDeviceSynchronize();
+    softmax_body_kernel<<<nsm, w * 32>>>(out, cyc, 0.37f, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(nsm);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost);
+    std::sort(h.begin(), h.end());
+    double elems = double(w) * 32 * (ITERS / 4) * 32;
+    printf("softmax body (FFMA2+2MUFU+FADD2+F2FP per pair) warps=%2d: %.2f exps/clk/SM (%s)\n", w, elems / double(h[nsm / 2]),
+           cudaGetErrorString(e));
+    cudaFree(out); cudaFree(cyc);
   }
   for (int w : {4, 8}) {
     int nsm = 148, reps = 2000;
