@@ -240,7 +240,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
 #endif
+#ifndef DSG_ATTN_NO_PINGPONG
     if (t == 1) named_bar_arrive(2, 256);          // ping-pong token: warpgroup 0 goes first
+#endif
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int qp = item % p.qpairs;
@@ -312,7 +314,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
         // MUFU ping-pong: the two warpgroups take turns in the exponential phase, so that the loads /
         // row-max / barrier phases of one always run under the other one's MUFU work
+#ifndef DSG_ATTN_NO_PINGPONG
         if (two) named_bar_sync(2 + t, 256);
+#endif
         ATT_T(4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -343,7 +347,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #endif
         }
         ATT_T(5);
+#ifndef DSG_ATTN_NO_PINGPONG
         if (two) named_bar_arrive(3 - t, 256);
+#endif
         l += (sum01.x + sum01.y) + (sum23.x + sum23.y);
         tmem_st_wait();
         tc_fence_before();

@@ -228,6 +228,32 @@ struct WeightSlot {
   std::vector<int64_t> shape;
 };
 
+// One activation workspace carved into the buffers of a forward pass, with the tensor maps that
+// describe them (valid for one (base pointer, batch, resolution) binding).
+struct WorkBufs {
+  void* base = nullptr;
+  int batch = 0, res = 0;
+  float* x = nullptr;               // fp32 residual stream [B*N, D]
+  __nv_bfloat16* abuf = nullptr;    // bf16 GEMM A operand [B*N, D] (LayerNorm / attention output)
+  __nv_bfloat16* qkv = nullptr;     // bf16 [B*N, 3D]
+  __nv_bfloat16* hid = nullptr;     // bf16 [B*N, hidden]; also im2col [B*P, 192] and head h1 fp32 [B*N, H1]
+  uint8_t* lowres = nullptr;        // [B*P]
+  CUtensorMap tm_im2col, tm_abuf, tm_hid, tm_qkv3d;                                  // A operands / attention
+  CUtensorMap tm_x_out, tm_x_patch, tm_pos_add, tm_qkv_out, tm_hid_out, tm_h1_out;   // GEMM outputs / addends
+};
+
+// predict_host pipeline lane: own stream, device staging and workspace, so that the copies of one
+// chunk of frames overlap the kernels of another
+struct HostLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  float* frames = nullptr; size_t frames_cap = 0;
+  void* ws = nullptr; size_t ws_cap = 0;
+  uint8_t* lowres = nullptr; size_t lowres_cap = 0;
+  int64_t* labels = nullptr; size_t labels_cap = 0;
+  WorkBufs bufs;
+};
+
 }  // namespace
 
 struct dinoseg {
@@ -257,16 +283,8 @@ struct dinoseg {
   float* pos = nullptr;
   size_t pos_cap = 0;
 
-  // workspace carve-up (valid for ws_ptr / ws_batch / ws_res)
-  void* ws_ptr = nullptr;
-  int ws_batch = 0, ws_res = 0;
-  float* x = nullptr;
-  __nv_bfloat16* abuf = nullptr;
-  __nv_bfloat16* qkv = nullptr;
-  __nv_bfloat16* hid = nullptr;
-  uint8_t* lowres_ws = nullptr;
-  CUtensorMap tm_im2col, tm_abuf, tm_hid, tm_qkv3d;           // GEMM A operands / attention input
-  CUtensorMap tm_x_out, tm_x_patch, tm_pos_add, tm_qkv_out, tm_hid_out, tm_h1_out, tm_abuf_out;  // GEMM outputs / addends
+  WorkBufs user;                    // binding of the caller-provided workspace (dinoseg_forward)
+  WorkBufs* last = nullptr;         // buffers of the most recent forward (dinoseg_copy_buffer)
 
   int debug_stop = 0;
   int launches = 0;
@@ -278,15 +296,11 @@ struct dinoseg {
   std::vector<int> ev_kind;          // kind of each recorded launch
   int ev_used = 0;
 
-  // predict_host staging (grow-only)
-  float* st_frames = nullptr;
-  size_t st_frames_cap = 0;
-  void* st_ws = nullptr;
-  size_t st_ws_cap = 0;
-  uint8_t* st_lowres = nullptr;
-  size_t st_lowres_cap = 0;
-  int64_t* st_labels = nullptr;
-  size_t st_labels_cap = 0;
+  // predict_host pipeline (lazily created)
+  static constexpr int kLanes = 2;
+  HostLane lanes[kLanes];
+  cudaEvent_t host_start = nullptr;
+  int host_chunk = 16;              // frames per pipeline chunk
 };
 
 namespace {
@@ -328,35 +342,35 @@ WsLayout ws_layout(const dinoseg* h, int batch) {
   return L;
 }
 
-int bind_workspace(dinoseg* h, void* ws, size_t ws_bytes, int batch) {
+int bind_workspace(dinoseg* h, WorkBufs& w, void* ws, size_t ws_bytes, int batch) {
   const WsLayout L = ws_layout(h, batch);
   if (ws_bytes < L.total) DSG_FAIL(h, "workspace too small: %zu < %zu bytes", ws_bytes, L.total);
   if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) DSG_FAIL(h, "workspace must be 1024-byte aligned");
-  if (h->ws_ptr == ws && h->ws_batch == batch && h->ws_res == h->res) return 0;
+  if (w.base == ws && w.batch == batch && w.res == h->res) return 0;
   uint8_t* base = static_cast<uint8_t*>(ws);
-  h->x = reinterpret_cast<float*>(base + L.x);
-  h->abuf = reinterpret_cast<__nv_bfloat16*>(base + L.abuf);
-  h->qkv = reinterpret_cast<__nv_bfloat16*>(base + L.qkv);
-  h->hid = reinterpret_cast<__nv_bfloat16*>(base + L.hid);
-  h->lowres_ws = base + L.lowres;
+  w.x = reinterpret_cast<float*>(base + L.x);
+  w.abuf = reinterpret_cast<__nv_bfloat16*>(base + L.abuf);
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(base + L.qkv);
+  w.hid = reinterpret_cast<__nv_bfloat16*>(base + L.hid);
+  w.lowres = base + L.lowres;
   const uint64_t M = uint64_t(batch) * h->Ntok;
   const uint64_t D = h->cfg.embed_dim;
-  bool ok = true;
   const uint64_t HID = h->cfg.mlp_hidden, H1 = h->cfg.head_h1;
-  ok &= make_tmap_gemm_a(&h->tm_im2col, h->hid, h->P, batch, 192);      // per frame: tiles never straddle frames
-  ok &= make_tmap_gemm_a(&h->tm_abuf, h->abuf, M, 1, D);
-  ok &= make_tmap_gemm_a(&h->tm_hid, h->hid, M, 1, HID);
-  ok &= make_tmap_qkv(&h->tm_qkv3d, h->qkv, batch, h->Ntok, 3 * D);
-  ok &= make_tmap_gemm_out(&h->tm_x_out, h->x, true, D, M, 1, D);
-  ok &= make_tmap_gemm_out(&h->tm_x_patch, h->x, true, D, h->Ntok, batch, D);
-  ok &= make_tmap_gemm_out(&h->tm_pos_add, h->pos, true, D, h->Ntok, 1, D);
-  ok &= make_tmap_gemm_out(&h->tm_qkv_out, h->qkv, false, 3 * D, M, 1, 3 * D);
-  ok &= make_tmap_gemm_out(&h->tm_hid_out, h->hid, false, HID, M, 1, HID);
-  ok &= make_tmap_gemm_out(&h->tm_h1_out, h->hid, true, H1, M, 1, H1);
+  bool ok = true;
+  ok &= make_tmap_gemm_a(&w.tm_im2col, w.hid, h->P, batch, 192);      // per frame: tiles never straddle frames
+  ok &= make_tmap_gemm_a(&w.tm_abuf, w.abuf, M, 1, D);
+  ok &= make_tmap_gemm_a(&w.tm_hid, w.hid, M, 1, HID);
+  ok &= make_tmap_qkv(&w.tm_qkv3d, w.qkv, batch, h->Ntok, 3 * D);
+  ok &= make_tmap_gemm_out(&w.tm_x_out, w.x, true, D, M, 1, D);
+  ok &= make_tmap_gemm_out(&w.tm_x_patch, w.x, true, D, h->Ntok, batch, D);
+  ok &= make_tmap_gemm_out(&w.tm_pos_add, h->pos, true, D, h->Ntok, 1, D);
+  ok &= make_tmap_gemm_out(&w.tm_qkv_out, w.qkv, false, 3 * D, M, 1, 3 * D);
+  ok &= make_tmap_gemm_out(&w.tm_hid_out, w.hid, false, HID, M, 1, HID);
+  ok &= make_tmap_gemm_out(&w.tm_h1_out, w.hid, true, H1, M, 1, H1);
   if (!ok) DSG_FAIL(h, "cuTensorMapEncodeTiled failed for the workspace tensor maps");
-  h->ws_ptr = ws;
-  h->ws_batch = batch;
-  h->ws_res = h->res;
+  w.base = ws;
+  w.batch = batch;
+  w.res = h->res;
   return 0;
 }
 
@@ -492,10 +506,16 @@ void dinoseg_destroy(dinoseg_t* h) {
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   if (h->pos) cudaFree(h->pos);
-  if (h->st_frames) cudaFree(h->st_frames);
-  if (h->st_ws) cudaFree(h->st_ws);
-  if (h->st_lowres) cudaFree(h->st_lowres);
-  if (h->st_labels) cudaFree(h->st_labels);
+  for (HostLane& l : h->lanes) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    if (l.frames) cudaFree(l.frames);
+    if (l.ws) cudaFree(l.ws);
+    if (l.lowres) cudaFree(l.lowres);
+    if (l.labels) cudaFree(l.labels);
+    if (l.done) cudaEventDestroy(l.done);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  if (h->host_start) cudaEventDestroy(h->host_start);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
@@ -565,7 +585,8 @@ int dinoseg_set_resolution(dinoseg_t* h, int resolution, void* stream) {
   h->P = g * g;
   h->Ntok = g * g + 1;
   h->p_rep = 480 / g;  // reference pl_torch_modules.py:297
-  h->ws_ptr = nullptr;  // tensor maps depend on Ntok
+  h->user.base = nullptr;  // tensor maps depend on Ntok
+  for (HostLane& l : h->lanes) l.bufs.base = nullptr;
   return 0;
 }
 
@@ -613,9 +634,9 @@ int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind,
   return 0;
 }
 
-int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprobs, uint8_t* lowres, int64_t* labels,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return -1;
+// Launch sequence of one forward pass over `batch` frames on the buffers of `w` (already bound).
+static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, int batch, float* logprobs, uint8_t* lowres,
+                        int64_t* labels, cudaStream_t s) {
   if (h->res == 0) DSG_FAIL(h, "dinoseg_forward: call dinoseg_set_resolution first");
   if (dinoseg_missing_weights(h) != 0) {
     std::string miss;
@@ -624,11 +645,9 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
     DSG_FAIL(h, "dinoseg_forward: %d parameters not set (first missing: %s)", dinoseg_missing_weights(h),
              miss.c_str());
   }
-  if (!frames || batch <= 0 || !workspace) DSG_FAIL(h, "dinoseg_forward: bad arguments");
+  if (!frames || batch <= 0) DSG_FAIL(h, "dinoseg_forward: bad arguments");
   if (size_t(batch) * h->Ntok > size_t(INT32_MAX) / 4) DSG_FAIL(h, "dinoseg_forward: batch too large");
-  DSG_CUDA(h, cudaSetDevice(h->device));
-  if (bind_workspace(h, workspace, workspace_bytes, batch) != 0) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  h->last = &w;
   const int D = h->cfg.embed_dim, HID = h->cfg.mlp_hidden, H = h->cfg.num_heads;
   const int M = batch * h->Ntok;
   const float eps = h->cfg.ln_eps;
@@ -645,66 +664,66 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
     p.col_scale = 1.f; p.scale_cols = 0;
     return p;
   };
-  { LaunchScope ls(h, K_IM2COL, s); DSG_CUDA(h, launch_im2col(frames, h->hid, batch, h->g, s)); ++n; }
+  { LaunchScope ls(h, K_IM2COL, s); DSG_CUDA(h, launch_im2col(frames, w.hid, batch, h->g, s)); ++n; }
   {
     LaunchScope ls(h, K_CLS, s);
-    cls_row_kernel<<<(batch * D + 255) / 256, 256, 0, s>>>(h->cls, h->pos, h->x, batch, h->Ntok, D);
+    cls_row_kernel<<<(batch * D + 255) / 256, 256, 0, s>>>(h->cls, h->pos, w.x, batch, h->Ntok, D);
     DSG_CUDA(h, cudaGetLastError()); ++n;
   }
   {
     GemmParams p = gp(D, 192, h->pe_b);
     p.rows_per_batch = h->P; p.batches = batch; p.row_off = 1;   // out row = b*Ntok + 1 + t, + pos[1 + t]
     LaunchScope ls(h, K_GEMM_PATCH, s);
-    DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, h->tm_im2col, h->tm_pe, h->tm_x_patch, h->tm_pos_add, p, sms, s)); ++n;
+    DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, w.tm_im2col, h->tm_pe, w.tm_x_patch, w.tm_pos_add, p, sms, s)); ++n;
   }
   if (stop == 1) { h->launches = n; return 0; }
 
   // ---- transformer blocks (vision_transformer.py:122-140) ----
   for (int i = 0; i < h->cfg.n_blocks; ++i) {
     BlockW& b = h->blocks[i];
-    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, b.ln1_g, b.ln1_b, h->abuf, M, D, eps, s)); ++n; }
+    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln1_g, b.ln1_b, w.abuf, M, D, eps, s)); ++n; }
     {
       GemmParams p = gp(3 * D, D, b.qkv_b);
       p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
       LaunchScope ls(h, K_GEMM_QKV, s);
-      DSG_CUDA(h, launch_gemm(EPI_BF16, h->tm_abuf, b.tm_qkv, h->tm_qkv_out, h->tm_qkv_out, p, sms, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_BF16, w.tm_abuf, b.tm_qkv, w.tm_qkv_out, w.tm_qkv_out, p, sms, s)); ++n;
     }
     if (stop == 2 + 3 * i) { h->launches = n; return 0; }
     {
       AttnParams p{};
-      p.B = batch; p.H = H; p.N = h->Ntok; p.D = D; p.out = h->abuf;
+      p.B = batch; p.H = H; p.N = h->Ntok; p.D = D; p.out = w.abuf;
       LaunchScope ls(h, K_ATTN, s);
-      DSG_CUDA(h, launch_attention(h->tm_qkv3d, p, h->num_sms, s)); ++n;
+      DSG_CUDA(h, launch_attention(w.tm_qkv3d, p, h->num_sms, s)); ++n;
     }
     {
       GemmParams p = gp(D, D, b.proj_b);
       LaunchScope ls(h, K_GEMM_PROJ, s);
-      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_abuf, b.tm_proj, h->tm_x_out, h->tm_x_out, p, sms, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_abuf, b.tm_proj, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
     }
     if (stop == 3 + 3 * i) { h->launches = n; return 0; }
-    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, b.ln2_g, b.ln2_b, h->abuf, M, D, eps, s)); ++n; }
+    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, s)); ++n; }
     {
       GemmParams p = gp(HID, D, b.fc1_b);
       LaunchScope ls(h, K_GEMM_FC1, s);
-      DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, h->tm_abuf, b.tm_fc1, h->tm_hid_out, h->tm_hid_out, p, sms, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, w.tm_abuf, b.tm_fc1, w.tm_hid_out, w.tm_hid_out, p, sms, s)); ++n;
     }
     {
       GemmParams p = gp(D, HID, b.fc2_b);
       LaunchScope ls(h, K_GEMM_FC2, s);
-      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, h->tm_hid, b.tm_fc2, h->tm_x_out, h->tm_x_out, p, sms, s)); ++n;
+      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_hid, b.tm_fc2, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
     }
     if (stop == 4 + 3 * i) { h->launches = n; return 0; }
   }
 
   // ---- final norm + head (vision_transformer.py:243, pl_torch_modules.py:243-255) ----
-  { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(h->x, h->norm_g, h->norm_b, h->abuf, M, D, eps, s)); ++n; }
-  float* h1 = reinterpret_cast<float*>(h->hid);
+  { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, h->norm_g, h->norm_b, w.abuf, M, D, eps, s)); ++n; }
+  float* h1 = reinterpret_cast<float*>(w.hid);
   {
     GemmParams p = gp(h->cfg.head_h1, D, h->h1_b);
     LaunchScope ls(h, K_GEMM_HEAD, s);
-    DSG_CUDA(h, launch_gemm(EPI_RELU_F32, h->tm_abuf, h->tm_h1, h->tm_h1_out, h->tm_h1_out, p, sms, s)); ++n;
+    DSG_CUDA(h, launch_gemm(EPI_RELU_F32, w.tm_abuf, h->tm_h1, w.tm_h1_out, w.tm_h1_out, p, sms, s)); ++n;
   }
-  uint8_t* lr = lowres ? lowres : h->lowres_ws;
+  uint8_t* lr = lowres ? lowres : w.lowres;
   {
     const size_t smem = head_tail_smem_bytes(h->cfg.head_h1);
     static bool attr[64] = {};
@@ -724,6 +743,16 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
   return 0;
 }
 
+int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprobs, uint8_t* lowres, int64_t* labels,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return -1;
+  if (h->res == 0) DSG_FAIL(h, "dinoseg_forward: call dinoseg_set_resolution first");
+  if (!frames || batch <= 0 || !workspace) DSG_FAIL(h, "dinoseg_forward: bad arguments");
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  if (bind_workspace(h, h->user, workspace, workspace_bytes, batch) != 0) return -1;
+  return forward_impl(h, h->user, frames, batch, logprobs, lowres, labels, static_cast<cudaStream_t>(stream));
+}
+
 int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
                          int64_t* host_labels, void* stream) {
   if (!h) return -1;
@@ -731,29 +760,68 @@ int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint
   if (!host_frames || batch <= 0) DSG_FAIL(h, "dinoseg_predict_host: bad arguments");
   DSG_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t fbytes = size_t(batch) * 3 * h->res * h->res * sizeof(float);
-  const size_t wbytes = dinoseg_workspace_bytes(h, batch);
-  const size_t lbytes = size_t(batch) * h->P;
+  // The batch is cut into chunks that go round-robin through two lanes (stream + staging + workspace
+  // each): H2D copy, forward and D2H copy of a chunk are ordered on its lane's stream, and the copies
+  // of one lane overlap the kernels of the other.  Frames are independent, so chunking does not change
+  // any result bit.
+  const int chunk = batch < h->host_chunk ? batch : h->host_chunk;
+  const size_t frame_elems = size_t(3) * h->res * h->res;
   const size_t W = size_t(h->g) * h->p_rep;
-  const size_t obytes = size_t(batch) * W * W * sizeof(int64_t);
-  auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
+  const size_t label_elems = W * W;
+  const size_t wbytes = dinoseg_workspace_bytes(h, chunk);
+  if (!h->host_start) DSG_CUDA(h, cudaEventCreateWithFlags(&h->host_start, cudaEventDisableTiming));
+  auto grow = [&](HostLane& l, void** p, size_t* cap, size_t need) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
-    if (*p) { cudaStreamSynchronize(s); cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (*p) { cudaStreamSynchronize(l.stream); cudaFree(*p); *p = nullptr; *cap = 0; }
     cudaError_t e = cudaMalloc(p, need);
     if (e == cudaSuccess) *cap = need;
     return e;
   };
-  DSG_CUDA(h, grow(reinterpret_cast<void**>(&h->st_frames), &h->st_frames_cap, fbytes));
-  DSG_CUDA(h, grow(&h->st_ws, &h->st_ws_cap, wbytes));
-  DSG_CUDA(h, grow(reinterpret_cast<void**>(&h->st_lowres), &h->st_lowres_cap, lbytes));
-  if (host_labels && obytes) DSG_CUDA(h, grow(reinterpret_cast<void**>(&h->st_labels), &h->st_labels_cap, obytes));
-  DSG_CUDA(h, cudaMemcpyAsync(h->st_frames, host_frames, fbytes, cudaMemcpyHostToDevice, s));
-  if (dinoseg_forward(h, h->st_frames, batch, nullptr, h->st_lowres, host_labels ? h->st_labels : nullptr, h->st_ws,
-                      h->st_ws_cap, s) != 0)
-    return -1;
-  if (host_lowres) DSG_CUDA(h, cudaMemcpyAsync(host_lowres, h->st_lowres, lbytes, cudaMemcpyDeviceToHost, s));
-  if (host_labels && obytes) DSG_CUDA(h, cudaMemcpyAsync(host_labels, h->st_labels, obytes, cudaMemcpyDeviceToHost, s));
-  DSG_CUDA(h, cudaStreamSynchronize(s));
+  const int nchunks = (batch + chunk - 1) / chunk;
+  const int nlanes = nchunks < dinoseg::kLanes ? nchunks : dinoseg::kLanes;
+  for (int k = 0; k < nlanes; ++k) {
+    HostLane& l = h->lanes[k];
+    if (!l.stream) DSG_CUDA(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    if (!l.done) DSG_CUDA(h, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    const size_t ws_before = l.ws_cap;
+    DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.frames), &l.frames_cap, size_t(chunk) * frame_elems * sizeof(float)));
+    DSG_CUDA(h, grow(l, &l.ws, &l.ws_cap, wbytes));
+    DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.lowres), &l.lowres_cap, size_t(chunk) * h->P));
+    if (host_labels && label_elems)
+      DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.labels), &l.labels_cap, size_t(chunk) * label_elems * sizeof(int64_t)));
+    if (l.ws_cap != ws_before) l.bufs.base = nullptr;
+  }
+  // lanes start after whatever the caller queued on its stream
+  DSG_CUDA(h, cudaEventRecord(h->host_start, s));
+  for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamWaitEvent(h->lanes[k].stream, h->host_start, 0));
+  for (int c = 0; c < nchunks; ++c) {
+    HostLane& l = h->lanes[c % nlanes];
+    const int f0 = c * chunk;
+    const int nb = (batch - f0) < chunk ? (batch - f0) : chunk;
+    DSG_CUDA(h, cudaMemcpyAsync(l.frames, host_frames + size_t(f0) * frame_elems, size_t(nb) * frame_elems * sizeof(float),
+                                cudaMemcpyHostToDevice, l.stream));
+    if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
+    if (forward_impl(h, l.bufs, l.frames, nb, nullptr, l.lowres, (host_labels && label_elems) ? l.labels : nullptr,
+                     l.stream) != 0)
+      return -1;
+    if (host_lowres)
+      DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
+                                  l.stream));
+    if (host_labels && label_elems)
+      DSG_CUDA(h, cudaMemcpyAsync(host_labels + size_t(f0) * label_elems, l.labels,
+                                  size_t(nb) * label_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
+  }
+  for (int k = 0; k < nlanes; ++k) {
+    DSG_CUDA(h, cudaEventRecord(h->lanes[k].done, h->lanes[k].stream));
+    DSG_CUDA(h, cudaStreamWaitEvent(s, h->lanes[k].done, 0));   // later work on the caller's stream is ordered after us
+  }
+  for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamSynchronize(h->lanes[k].stream));
+  return 0;
+}
+
+int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk) {
+  if (!h || frames_per_chunk < 1) return -1;
+  h->host_chunk = frames_per_chunk;
   return 0;
 }
 
@@ -772,12 +840,13 @@ int64_t dinoseg_copy_buffer(dinoseg_t* h, const char* name, void* dst, size_t ds
   if (!h || !name || !dst) return -1;
   const void* src = nullptr;
   size_t bytes = 0;
-  const size_t M = size_t(h->ws_batch) * h->Ntok, D = h->cfg.embed_dim;
+  const WorkBufs* w = h->last;
+  const size_t M = size_t(w ? w->batch : 0) * h->Ntok, D = h->cfg.embed_dim;
   const std::string nm(name);
   if (nm == "pos") { src = h->pos; bytes = size_t(h->Ntok) * D * 4; }
-  else if (nm == "x") { src = h->x; bytes = M * D * 4; }
-  else if (nm == "abuf") { src = h->abuf; bytes = M * D * 2; }
-  else if (nm == "qkv") { src = h->qkv; bytes = M * 3 * D * 2; }
+  else if (nm == "x") { src = w ? w->x : nullptr; bytes = M * D * 4; }
+  else if (nm == "abuf") { src = w ? w->abuf : nullptr; bytes = M * D * 2; }
+  else if (nm == "qkv") { src = w ? w->qkv : nullptr; bytes = M * 3 * D * 2; }
   else DSG_FAIL(h, "dinoseg_copy_buffer: unknown buffer '%s'", name);
   if (!src || bytes == 0) DSG_FAIL(h, "dinoseg_copy_buffer: buffer '%s' not available yet", name);
   if (bytes > dst_bytes) DSG_FAIL(h, "dinoseg_copy_buffer: destination too small (%zu < %zu)", dst_bytes, bytes);

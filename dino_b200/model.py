@@ -343,12 +343,13 @@ class DINOSeg(nn.Module):
         _, _, lab = self.infer(frames, want_logprobs=False, want_labels=True)
         return lab[0].cpu().numpy()
 
-    def predict_batch(self, frames, output="labels"):
+    def predict_batch(self, frames, output="labels", out=None):
         """Batched counterpart of predict() for already-normalised frames [B,3,r,r].
 
         Device frames -> device result (asynchronous).  Host frames (ideally pinned) go through
-        the library's host entry point, which copies in, runs, copies out and synchronises ->
-        numpy result.  output: 'labels' (int64 [B,g*p,g*p]) or 'lowres' (uint8 [B,g,g])."""
+        the library's host entry point, which pipelines H2D copy / kernels / D2H copy over chunks of
+        the batch and synchronises -> numpy result.  output: 'labels' (int64 [B,g*p,g*p]) or 'lowres'
+        (uint8 [B,g,g]).  out: optional preallocated (pinned) host tensor to receive the result."""
         if output not in ("labels", "lowres"):
             raise ValueError(output)
         if frames.device.type == "cuda":
@@ -361,14 +362,16 @@ class DINOSeg(nn.Module):
         self._ensure_resolution(lib, res)
         g = res // 8
         p = 480 // g
-        pin = torch.cuda.is_available()
-        low = torch.empty((b, g, g), dtype=torch.uint8, pin_memory=pin) if output == "lowres" else None
-        lab = torch.empty((b, g * p, g * p), dtype=torch.int64, pin_memory=pin) if output == "labels" else None
+        shape, dtype = ((b, g * p, g * p), torch.int64) if output == "labels" else ((b, g, g), torch.uint8)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+        elif tuple(out.shape) != shape or out.dtype != dtype or out.device.type != "cpu" or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous CPU tensor of shape {shape} and dtype {dtype}")
         rc = lib.dinoseg_predict_host(self._handle, frames.data_ptr(), b,
-                                      low.data_ptr() if low is not None else None,
-                                      lab.data_ptr() if lab is not None else None, self._stream())
+                                      out.data_ptr() if output == "lowres" else None,
+                                      out.data_ptr() if output == "labels" else None, self._stream())
         self._check(rc, "dinoseg_predict_host")
-        return (lab if output == "labels" else low).numpy()
+        return out.numpy()
 
     def profile_enable(self, on=True, kinds=None):
         """Bracket kernel launches of the following forwards with CUDA events (on the launching
