@@ -29,6 +29,7 @@ enum : int {
   EPI_RESID_F32 = 2,  // out f32 = addend + acc + bias      (addend = out: in-place residual add)
   EPI_PATCH_F32 = 3,  // out f32[b, 1 + t] = acc + bias + pos[1 + t]   (addend = positional table)
   EPI_RELU_F32 = 4,   // out f32 = relu(acc + bias)
+  EPI_RELU_SPLIT_BF16 = 5,  // v = relu(acc + bias); out bf16 [rows, 3*split_part] = [hi(v) | lo(v) | hi(v)] (bf16x3 operand)
 };
 
 struct GemmParams {
@@ -40,6 +41,7 @@ struct GemmParams {
   const float* bias;    // [N] (may be null)
   float col_scale;
   int scale_cols;
+  int split_part;       // EPI_RELU_SPLIT_BF16: width of each of the three output parts (multiple of 64)
 };
 
 constexpr int GEMM_BM = 128;
@@ -51,10 +53,14 @@ constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;   // 24 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 128 * 128;             // one staging buffer: 128 rows x 128 bytes
 
-__host__ __device__ constexpr bool gemm_out_is_f32(int epi) { return epi >= EPI_RESID_F32; }
+__host__ __device__ constexpr bool gemm_out_is_f32(int epi) {
+  return epi == EPI_RESID_F32 || epi == EPI_PATCH_F32 || epi == EPI_RELU_F32;
+}
 __host__ __device__ constexpr bool gemm_has_addend(int epi) { return epi == EPI_RESID_F32 || epi == EPI_PATCH_F32; }
-__host__ __device__ constexpr int gemm_stages(int epi) { return gemm_out_is_f32(epi) ? 3 : 4; }
-__host__ __device__ constexpr int gemm_nbuf(int epi) { return gemm_out_is_f32(epi) ? 4 : 2; }
+__host__ __device__ constexpr int gemm_nbuf(int epi) {
+  return (gemm_out_is_f32(epi) || epi == EPI_RELU_SPLIT_BF16) ? 4 : 2;
+}
+__host__ __device__ constexpr int gemm_stages(int epi) { return gemm_nbuf(epi) == 4 ? 3 : 4; }
 __host__ __device__ constexpr size_t gemm_smem_bytes(int epi) {
   return size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES + size_t(gemm_nbuf(epi)) * GEMM_STG_BYTES + 1024 /*align*/ + 256;
 }
@@ -84,6 +90,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const GemmParams p) {
   constexpr bool OUT_F32 = gemm_out_is_f32(EPI);
   constexpr bool HAS_ADD = gemm_has_addend(EPI);
+  constexpr bool SPLIT = EPI == EPI_RELU_SPLIT_BF16;
+  constexpr int BPC = SPLIT ? 2 : 1;             // staging buffers per chunk
   constexpr int STAGES = gemm_stages(EPI);
   constexpr int NBUF = gemm_nbuf(EPI);
   constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 bytes per row)
@@ -219,7 +227,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = 0; c < NCH; ++c, ++g) {
         int col0, r0, bt;
         chunk_coords(g, col0, r0, bt);
-        const int b = g % NBUF;
+        const int b = (g * BPC) % NBUF;
         uint8_t* sb = stg + size_t(b) * GEMM_STG_BYTES;
         // accumulator chunk -> registers
         float v[CH];
@@ -249,7 +257,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // staging buffer b: the TMA store that last read it (chunk g - NBUF) must be done, and for
         // addend epilogues the prefetch of chunk g + PD goes into the buffer of chunk g + PD - NBUF
         if (leader) {
-          tma_store_wait_read<NBUF - PD - 1>();
+          tma_store_wait_read<NBUF / BPC - PD - 1>();
           if (HAS_ADD && g + PD < total_chunks) issue_add(g + PD);
         }
         if constexpr (HAS_ADD) {
@@ -279,6 +287,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 8; ++j) {
               float x = v[8 * k + j];
               if constexpr (EPI == EPI_GELU_BF16) x = gelu_erf(x);
+              else if constexpr (SPLIT) x = fmaxf(x, 0.f);
               else if (col0 + 8 * k + j < p.scale_cols) x *= p.col_scale;
               w[j] = x;
             }
@@ -286,12 +295,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
             q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
             *reinterpret_cast<uint4*>(srow + ((k ^ (row & 7)) << 4)) = q;
+            if constexpr (SPLIT) {
+              uint4 l;   // lo = bf16(v - hi)
+              l.x = pack_bf16x2(w[0] - __uint_as_float(q.x << 16), w[1] - __uint_as_float(q.x & 0xffff0000u));
+              l.y = pack_bf16x2(w[2] - __uint_as_float(q.y << 16), w[3] - __uint_as_float(q.y & 0xffff0000u));
+              l.z = pack_bf16x2(w[4] - __uint_as_float(q.z << 16), w[5] - __uint_as_float(q.z & 0xffff0000u));
+              l.w = pack_bf16x2(w[6] - __uint_as_float(q.w << 16), w[7] - __uint_as_float(q.w & 0xffff0000u));
+              *reinterpret_cast<uint4*>(srow + GEMM_STG_BYTES + ((k ^ (row & 7)) << 4)) = l;
+            }
           }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (leader) {
-          if (col0 < p.N) tma_store_3d(&tmOut, sb, col0, p.row_off + r0, bt);
+          if constexpr (SPLIT) {
+            if (col0 < p.split_part) {
+              tma_store_3d(&tmOut, sb, col0, p.row_off + r0, bt);
+              tma_store_3d(&tmOut, sb + GEMM_STG_BYTES, p.split_part + col0, p.row_off + r0, bt);
+              tma_store_3d(&tmOut, sb, 2 * p.split_part + col0, p.row_off + r0, bt);
+            }
+          } else {
+            if (col0 < p.N) tma_store_3d(&tmOut, sb, col0, p.row_off + r0, bt);
+          }
           tma_store_commit();
         }
       }

@@ -14,13 +14,23 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
   for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
 }
 
-// W2 [H2, H1] (nn.Linear layout) -> W2t [H1, H2P] fp32, zero padded columns
-__global__ void transpose_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int H2, int H1,
-                                     int H2P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= H1 * H2P) return;
-  const int k = i / H2P, n = i - k * H2P;
-  out[i] = n < H2 ? in[size_t(n) * H1 + k] : 0.f;
+// "bf16x3" operand split.  A product x*w with both operands rounded to bf16 carries a 2^-9 relative
+// error; writing x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) and using
+//     x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+// brings it to ~2^-16 while staying on the bf16 tensor cores: the three products are obtained from ONE
+// GEMM of three-fold K by laying the operands out as A' = [hi | lo | hi], W' = [hi | hi | lo].  Used for the
+// segmentation head (0.7 % of the FLOPs), whose bf16 rounding otherwise dominates the log-prob error.
+// W [N, K] fp32 -> W' [N, 3*Kp] bf16 (each part zero padded from K to Kp columns)
+__global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int Kp) {
+  const size_t total = size_t(N) * Kp;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int n = int(i / Kp), k = int(i - size_t(n) * Kp);
+    float v = k < K ? w[size_t(n) * K + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + size_t(n) * 3 * Kp + k;
+    o[0] = hi; o[Kp] = hi; o[2 * Kp] = lo;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -78,9 +88,23 @@ __global__ void posembed_bicubic_kernel(const float* __restrict__ pos_src /*[G0*
 
 // ---------------------------------------------------------------------------------------
 // im2col for the 8x8/stride-8 patch-embed conv (reference vision_transformer.py:153,157):
-//   A[b*P + i*g + j][c*64 + ky*8 + kx] = bf16(frame[b][c][i*8+ky][j*8+kx])
-// One thread moves two image rows of one patch (2 x 32 B in, one 32 B chunk out).
+//   A[b*P + i*g + j][c*64 + ky*8 + kx] = frame[b][c][i*8+ky][j*8+kx]
+// written as a bf16x3 operand [hi | lo | hi] (3 x 192 columns, see split_weight_kernel): the rounding of
+// the pixels / conv weights to plain bf16 is the largest single contribution to the final log-prob error.
+// One thread moves two image rows of one patch (2 x 32 B in, 3 x 32 B out).
 // ---------------------------------------------------------------------------------------
+constexpr int IM2COL_K = 192;
+constexpr int IM2COL_K3 = 3 * IM2COL_K;
+
+__device__ __forceinline__ void split_pack8(const float4& a0, const float4& a1, uint4& hi, uint4& lo) {
+  hi.x = pack_bf16x2(a0.x, a0.y); hi.y = pack_bf16x2(a0.z, a0.w);
+  hi.z = pack_bf16x2(a1.x, a1.y); hi.w = pack_bf16x2(a1.z, a1.w);
+  lo.x = pack_bf16x2(a0.x - __uint_as_float(hi.x << 16), a0.y - __uint_as_float(hi.x & 0xffff0000u));
+  lo.y = pack_bf16x2(a0.z - __uint_as_float(hi.y << 16), a0.w - __uint_as_float(hi.y & 0xffff0000u));
+  lo.z = pack_bf16x2(a1.x - __uint_as_float(hi.z << 16), a1.y - __uint_as_float(hi.z & 0xffff0000u));
+  lo.w = pack_bf16x2(a1.z - __uint_as_float(hi.w << 16), a1.w - __uint_as_float(hi.w & 0xffff0000u));
+}
+
 __global__ void im2col_patch8_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ A, int B,
                                      int g) {
   const int r = g * 8;
@@ -97,14 +121,16 @@ __global__ void im2col_patch8_kernel(const float* __restrict__ frames, __nv_bflo
   const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + 4));
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(src + r));
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(src + r + 4));
-  uint4 o0, o1;
-  o0.x = pack_bf16x2(a0.x, a0.y); o0.y = pack_bf16x2(a0.z, a0.w);
-  o0.z = pack_bf16x2(a1.x, a1.y); o0.w = pack_bf16x2(a1.z, a1.w);
-  o1.x = pack_bf16x2(b0.x, b0.y); o1.y = pack_bf16x2(b0.z, b0.w);
-  o1.z = pack_bf16x2(b1.x, b1.y); o1.w = pack_bf16x2(b1.z, b1.w);
-  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * 192 + c * 64 + kyp * 16;
-  *reinterpret_cast<uint4*>(dst) = o0;
-  *reinterpret_cast<uint4*>(dst + 8) = o1;
+  uint4 h0, l0, h1, l1;
+  split_pack8(a0, a1, h0, l0);
+  split_pack8(b0, b1, h1, l1);
+  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * IM2COL_K3 + c * 64 + kyp * 16;
+  *reinterpret_cast<uint4*>(dst) = h0;
+  *reinterpret_cast<uint4*>(dst + 8) = h1;
+  *reinterpret_cast<uint4*>(dst + IM2COL_K) = l0;
+  *reinterpret_cast<uint4*>(dst + IM2COL_K + 8) = l1;
+  *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K) = h0;
+  *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K + 8) = h1;
 }
 
 // x[b*Ntok + 0, :] = cls + pos[0]      (reference vision_transformer.py:229-233)
@@ -120,7 +146,8 @@ __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __res
 // LayerNorm (eps inside the sqrt, biased variance; reference :114,:118,:183 with eps=1e-6 :303)
 // fp32 in -> bf16 out (the bf16 copy is the A operand of the following GEMM).  One warp per row.
 // ---------------------------------------------------------------------------------------
-template <int D>
+// SPLIT: y is [M, 3*D] = [hi | lo | hi] (bf16x3 operand of the head GEMM, see split_weight_kernel).
+template <int D, bool SPLIT>
 __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       __nv_bfloat16* __restrict__ y, int M, float eps) {
@@ -149,15 +176,24 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq * (1.0f / D) + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + size_t(row) * D);
+  uint2* yr = reinterpret_cast<uint2*>(y + size_t(row) * (SPLIT ? 3 * D : D));
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
     const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    const float a = (v[i].x - mean) * rstd * gm.x + bt.x, b = (v[i].y - mean) * rstd * gm.y + bt.y;
+    const float c = (v[i].z - mean) * rstd * gm.z + bt.z, d = (v[i].w - mean) * rstd * gm.w + bt.w;
     uint2 o;
-    o.x = pack_bf16x2((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y);
-    o.y = pack_bf16x2((v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
+    o.x = pack_bf16x2(a, b);
+    o.y = pack_bf16x2(c, d);
     yr[i * 32 + lane] = o;
+    if constexpr (SPLIT) {
+      uint2 l;
+      l.x = pack_bf16x2(a - __uint_as_float(o.x << 16), b - __uint_as_float(o.x & 0xffff0000u));
+      l.y = pack_bf16x2(c - __uint_as_float(o.y << 16), d - __uint_as_float(o.y & 0xffff0000u));
+      yr[D / 4 + i * 32 + lane] = l;
+      yr[2 * (D / 4) + i * 32 + lane] = o;
+    }
   }
 }
 
@@ -178,117 +214,61 @@ __device__ __forceinline__ int argmax_first(const float* v, int C) {
 constexpr int HEAD_MAX_C = 16;
 
 // ---------------------------------------------------------------------------------------
-// Head tail: h1 (= relu(layer_1), fp32, produced by the tensor-core GEMM) -> layer_2 -> relu ->
-// layer_3 -> log_softmax -> argmax   (reference pl_torch_modules.py:119-123, :295), fp32 CUDA cores.
+// Head tail: h2 (= relu(layer_2(relu(layer_1))), fp32, produced by the two tensor-core GEMMs) ->
+// layer_3 -> log_softmax -> argmax   (reference pl_torch_modules.py:121-123, :295), fp32 CUDA cores.
 // Input rows are tokens INCLUDING the cls row of every frame; output rows drop it (reference :243).
-// Block = 256 threads = 64 patch rows; W2^T (padded) and the h1 tile live in shared memory.
+// One thread per patch row; W3 / b3 live in shared memory.
 // ---------------------------------------------------------------------------------------
-constexpr int HT_ROWS = 64;
-constexpr int HT_H2P = 112;  // layer-2 width padded to 7 x 16
+constexpr int HT_MAX_H2 = 104;
 
-__host__ __device__ constexpr size_t head_tail_smem_bytes(int H1) {
-  return size_t(H1) * HT_H2P * 4 + size_t(HT_ROWS) * (H1 + 1) * 4 + HEAD_MAX_C * 104 * 4 + (HT_H2P + HEAD_MAX_C) * 4;
-}
-
-__global__ void __launch_bounds__(256, 1)
-head_tail_kernel(const float* __restrict__ h1 /*[B*Ntok, H1]*/, const float* __restrict__ w2t /*[H1, HT_H2P]*/,
-                 const float* __restrict__ b2 /*[H2]*/, const float* __restrict__ w3 /*[C, H2]*/,
+__global__ void __launch_bounds__(256)
+head_tail_kernel(const float* __restrict__ h2 /*[B*Ntok, H2]*/, const float* __restrict__ w3 /*[C, H2]*/,
                  const float* __restrict__ b3 /*[C]*/, float* __restrict__ logprobs /*[B*P, C] or null*/,
-                 uint8_t* __restrict__ lowres /*[B*P] or null*/, int B, int P, int Ntok, int H1, int H2, int C) {
-  extern __shared__ float sm[];
-  float* sW2 = sm;                              // [H1][HT_H2P]
-  float* sH = sW2 + size_t(H1) * HT_H2P;        // [64][H1+1]  (later reused as h2 [64][105])
-  float* sW3 = sH + size_t(HT_ROWS) * (H1 + 1); // [C][104]
-  float* sB2 = sW3 + HEAD_MAX_C * 104;          // [HT_H2P]
-  float* sB3 = sB2 + HT_H2P;                    // [HEAD_MAX_C]
-  const int tid = threadIdx.x;
-  const int ldh = H1 + 1;
+                 uint8_t* __restrict__ lowres /*[B*P] or null*/, int B, int P, int Ntok, int H2, int C) {
+  __shared__ float sW3[HEAD_MAX_C * HT_MAX_H2];
+  __shared__ float sB3[HEAD_MAX_C];
+  for (int i = threadIdx.x; i < HEAD_MAX_C * HT_MAX_H2; i += blockDim.x) {
+    const int c = i / HT_MAX_H2, k = i - c * HT_MAX_H2;
+    sW3[i] = (c < C && k < H2) ? w3[c * H2 + k] : 0.f;
+  }
+  if (threadIdx.x < HEAD_MAX_C) sB3[threadIdx.x] = threadIdx.x < C ? b3[threadIdx.x] : 0.f;
+  __syncthreads();
   const int total_rows = B * P;
-  const int ntiles = (total_rows + HT_ROWS - 1) / HT_ROWS;
-
-  // weights once per (persistent) block
-  for (int i = tid; i < H1 * HT_H2P; i += 256) sW2[i] = w2t[i];
-  for (int i = tid; i < C * H2; i += 256) sW3[(i / H2) * 104 + (i % H2)] = w3[i];
-  for (int i = tid; i < HT_H2P; i += 256) sB2[i] = i < H2 ? b2[i] : 0.f;
-  if (tid < C) sB3[tid] = b3[tid];
-
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * HT_ROWS;
-    __syncthreads();  // previous tile's readers of sH are done (and weights are visible)
-    for (int i = tid; i < HT_ROWS * H1; i += 256) {
-      const int rr = i / H1, k = i - rr * H1;
-      const int r = r0 + rr;
-      float v = 0.f;
-      if (r < total_rows) {
-        const int b = r / P, t = r - b * P;
-        v = h1[(size_t(b) * Ntok + 1 + t) * H1 + k];
-      }
-      sH[rr * ldh + k] = v;
-    }
-    __syncthreads();
-
-    // layer 2: each thread -> 4 rows x 7 columns (tx + 16c)
-    float acc[4][7];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_rows; r += gridDim.x * blockDim.x) {
+    const int b = r / P, t = r - b * P;
+    const float4* src = reinterpret_cast<const float4*>(h2 + (size_t(b) * Ntok + 1 + t) * H2);
+    float z[HEAD_MAX_C];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int c = 0; c < HEAD_MAX_C; ++c) z[c] = 0.f;
+    for (int k4 = 0; k4 < H2 / 4; ++k4) {
+      const float4 hv = __ldg(src + k4);
 #pragma unroll
-      for (int c = 0; c < 7; ++c) acc[a][c] = 0.f;
-    for (int k = 0; k < H1; ++k) {
-      float a[4], w[7];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sH[(ty * 4 + i) * ldh + k];
-#pragma unroll
-      for (int c = 0; c < 7; ++c) w[c] = sW2[k * HT_H2P + tx + 16 * c];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < 7; ++c) acc[i][c] = fmaf(a[i], w[c], acc[i][c]);
-    }
-    __syncthreads();  // everyone is done reading sH (h1)
-    float* sH2 = sH;  // [64][105]
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        const int n = tx + 16 * c;
-        if (n < 104) sH2[(ty * 4 + i) * 105 + n] = fmaxf(acc[i][c] + sB2[n], 0.f);
-      }
-    __syncthreads();
-
-    // layer 3 + log_softmax + argmax: one thread per row
-    if (tid < HT_ROWS) {
-      const int r = r0 + tid;
-      if (r < total_rows) {
-        float z[HEAD_MAX_C];
-#pragma unroll
-        for (int c = 0; c < HEAD_MAX_C; ++c) z[c] = 0.f;
-        for (int k = 0; k < H2; ++k) {
-          const float hv = sH2[tid * 105 + k];
-#pragma unroll
-          for (int c = 0; c < HEAD_MAX_C; ++c)
-            if (c < C) z[c] = fmaf(hv, sW3[c * 104 + k], z[c]);
+      for (int c = 0; c < HEAD_MAX_C; ++c) {
+        if (c < C) {
+          const float* wr = sW3 + c * HT_MAX_H2 + 4 * k4;
+          z[c] = fmaf(hv.x, wr[0], z[c]); z[c] = fmaf(hv.y, wr[1], z[c]);
+          z[c] = fmaf(hv.z, wr[2], z[c]); z[c] = fmaf(hv.w, wr[3], z[c]);
         }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < HEAD_MAX_C; ++c)
-          if (c < C) { z[c] += sB3[c]; mx = fmaxf(mx, z[c]); }
-        float se = 0.f;
-#pragma unroll
-        for (int c = 0; c < HEAD_MAX_C; ++c)
-          if (c < C) se += expf(z[c] - mx);
-        const float lse = logf(se);
-#pragma unroll
-        for (int c = 0; c < HEAD_MAX_C; ++c)
-          if (c < C) z[c] = (z[c] - mx) - lse;
-        if (logprobs != nullptr) {
-#pragma unroll
-          for (int c = 0; c < HEAD_MAX_C; ++c)
-            if (c < C) logprobs[size_t(r) * C + c] = z[c];
-        }
-        if (lowres != nullptr) lowres[r] = uint8_t(argmax_first(z, C));
       }
     }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_C; ++c)
+      if (c < C) { z[c] += sB3[c]; mx = fmaxf(mx, z[c]); }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_C; ++c)
+      if (c < C) se += expf(z[c] - mx);
+    const float lse = logf(se);
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_C; ++c)
+      if (c < C) z[c] = (z[c] - mx) - lse;
+    if (logprobs != nullptr) {
+#pragma unroll
+      for (int c = 0; c < HEAD_MAX_C; ++c)
+        if (c < C) logprobs[size_t(r) * C + c] = z[c];
+    }
+    if (lowres != nullptr) lowres[r] = uint8_t(argmax_first(z, C));
   }
 }
 

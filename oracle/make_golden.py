@@ -38,6 +38,7 @@ CASES = [
     ("s8_nb1_64_trained", "vit_small", 1, 64, 3, "trained_like", 4),
     ("s8_nb3_480_refinit", "vit_small", 3, 480, 1, "reference_init", 5),
     ("b8_nb4_240_trained", "vit_base", 4, 240, 1, "trained_like", 6),
+    ("b8_nb4_240_refinit", "vit_base", 4, 240, 1, "reference_init", 8),
 ]
 
 

@@ -10,7 +10,9 @@ Tolerances (bf16 tensor-core operands, fp32 accumulation / residual stream / LN 
   * per-patch log-probs: max-abs error <= TOL_ABS[variant], where 'reference_init' are the weights
     BASELINE.json names (near-uniform log-probs in [-2.4,-1.5]) and 'trained_like' is a stress
     variant with O(10)-magnitude logits, judged relative to the log-prob range;
-  * label maps: >= 99.5 % of the pixels equal to the reference's;
+  * label maps: >= 99.5 % of the pixels equal to the reference's for 'reference_init' weights (>= 98.5 % for
+    the 'trained_like' stress weights), and EVERY differing patch must be a near-tie of the reference
+    (top-2 log-prob margin below twice the max log-prob error);
   * argmax + replication on identical log-probs: bit-exact.
 """
 import ctypes as C
@@ -27,9 +29,17 @@ from oracle import dinoseg_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL_ABS_REFINIT = 5e-3          # expected 2e-3 with this precision recipe
+TOL_ABS_REFINIT = 2e-3          # measured 3.5e-4 .. 7.5e-4 (SURVEY.md §7.3 expected 2e-3 for plain bf16 operands)
 TOL_REL_TRAINED = 1.5e-2        # of the reference log-prob range (max - min)
-MIN_LABEL_AGREEMENT = 0.995
+MIN_LABEL_AGREEMENT = 0.995     # BASELINE.json north_star, for the random-init weights it names
+MIN_LABEL_AGREEMENT_STRESS = 0.985   # 'trained_like' stress weights: many exact near-ties by construction
+
+
+def _agreement_ok(got, ref):
+    """>= 99.5 % of the patches equal; inputs with fewer than 400 patches may differ in at most 2
+    (one near-tie there already costs more than 0.5 %)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    return float((got == ref).mean()) >= MIN_LABEL_AGREEMENT or int((got != ref).sum()) <= (2 if got.size < 400 else 0)
 STATS_PATH = os.path.join(ROOT, "gpurun_out", "parity_stats.jsonl")
 
 
@@ -93,7 +103,7 @@ def test_against_reference_golden(name):
     max_abs = _compare_logprobs(name, lp, gd["logprobs"], meta["variant"])
     agree = float((low == gd["low"]).mean())
     _record(case=name, label_agreement=agree)
-    assert agree >= MIN_LABEL_AGREEMENT, (name, agree)
+    assert agree >= (MIN_LABEL_AGREEMENT if meta["variant"] == "reference_init" else MIN_LABEL_AGREEMENT_STRESS), (name, agree)
     # every disagreeing patch must be a near-tie of the reference (top-2 margin below twice the error)
     srt = np.sort(gd["logprobs"], axis=1)
     margin = (srt[:, -1] - srt[:, -2]).reshape(low.shape)
@@ -188,7 +198,12 @@ def test_against_oracle_edge_resolutions(res, nb, batch):
     ref_low, ref_high = O.labels_from_logprobs(torch.from_numpy(ref), batch, g)
     _compare_logprobs(f"oracle_{res}", lp.cpu().numpy(), ref, "reference_init")
     assert tuple(lab.shape) == tuple(ref_high.shape)
-    assert float((low.cpu().numpy() == ref_low).mean()) >= MIN_LABEL_AGREEMENT
+    assert _agreement_ok(low.cpu().numpy(), ref_low)
+    # every disagreeing patch is a near-tie of the oracle (top-2 margin below twice the max error)
+    srt = np.sort(ref, axis=1)
+    margin = (srt[:, -1] - srt[:, -2]).reshape(ref_low.shape)
+    err = float(np.abs(lp.cpu().numpy() - ref).max())
+    assert (margin[low.cpu().numpy() != ref_low] <= 2 * err + 1e-6).all()
     assert (lab.cpu().numpy() == np.kron(low.cpu().numpy(), np.ones((1, p, p), dtype=np.int64))).all()
 
 
