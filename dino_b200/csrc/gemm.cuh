@@ -6,12 +6,13 @@
 //   patch-embed (reference vision_transformer.py:153-157 as an im2col GEMM), qkv (:75,:82),
 //   proj (:77,:105), fc1/GELU (:54-55,:60-61), fc2 (:56,:63), head layer_1 (pl_torch_modules.py:113,118).
 //
-// Persistent, warp-specialised (192 threads, 1 CTA per SM, tile = 128 x 192, n-tiles fastest so the
+// Persistent, warp-specialised (320 threads, 1 CTA per SM, tile = 128 x 192, n-tiles fastest so the
 // CTAs that run concurrently share their A rows through L2):
 //   warp 0      : TMA producer  (A tile 128x64, W tile 192x64 per k-block, SWIZZLE_128B, ring of STAGES)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulator stages
 //                 (2 x 192 fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2..5  : epilogue: tcgen05.ld (one accumulator row per thread) -> bias / activation / addend
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter, each taking half of a chunk's columns):
+//                 tcgen05.ld (one accumulator row segment per thread) -> bias / activation / addend
 //                 -> swizzled shared-memory staging -> TMA store (fully coalesced, tails clipped by
 //                 the tensor map).  Addends (residual stream, positional table) are TMA-loaded into
 //                 the same staging buffers two chunks ahead.
@@ -47,7 +48,8 @@ struct GemmParams {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 192;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_THREADS = 256;                 // 8 epilogue warps: two per TMEM lane quarter
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;   // 24 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
@@ -107,7 +109,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + size_t(NBUF) * GEMM_STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;       // 2
-  uint64_t* acc_empty = acc_full + 2;            // 2 (4 arrivals: one per epilogue warp)
+  uint64_t* acc_empty = acc_full + 2;            // 2 (8 arrivals: one per epilogue warp)
   uint64_t* add_bar = acc_empty + 2;             // NBUF
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + NBUF);
 
@@ -132,7 +134,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], GEMM_EPI_THREADS / 32);
     }
     for (int s = 0; s < NBUF; ++s) mbar_init(&add_bar[s], 1);
     fence_mbar_init();
@@ -191,8 +193,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ---------------- epilogue: thread <-> accumulator row ----------------
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;              // which half of every chunk's columns this warp handles
     const int row = quarter * 32 + lane;
     const bool leader = threadIdx.x == 64;
+    constexpr int HC = CH / 2;                     // columns per thread per chunk (32 bf16 / 16 fp32 = 64 bytes)
     const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
     const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
     const int total_chunks = my_tiles * NCH;
@@ -229,15 +233,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         chunk_coords(g, col0, r0, bt);
         const int b = (g * BPC) % NBUF;
         uint8_t* sb = stg + size_t(b) * GEMM_STG_BYTES;
-        // accumulator chunk -> registers
-        float v[CH];
+        const int colh = col0 + half * HC;         // first global column of this thread's segment
+        // accumulator segment -> registers
+        float v[HC];
         __syncwarp();
-#pragma unroll
-        for (int h = 0; h < CH / 32; ++h) {
+        if constexpr (HC == 32) {
           uint32_t r[32];
-          tmem_ld_x32(acc + uint32_t(c * CH + h * 32), r);
+          tmem_ld_x32(acc + uint32_t(c * CH + half * HC), r);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[h * 32 + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_x16(acc + uint32_t(c * CH + half * HC), r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         }
         tmem_ld_wait();
         if (c == NCH - 1) {
@@ -247,9 +256,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < CH; i += 4) {
-            if (col0 + i < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+          for (int i = 0; i < HC; i += 4) {
+            if (colh + i < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + colh + i));
               v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
           }
@@ -263,13 +272,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (HAS_ADD) {
           mbar_wait(&add_bar[b], (g / NBUF) & 1);
         } else {
-          named_bar_sync(1, 128);
+          named_bar_sync(1, GEMM_EPI_THREADS);
         }
+        // 128-byte staging row = 8 x 16-byte segments, XOR-swizzled with the row index (SWIZZLE_128B);
+        // this thread owns segments half*4 .. half*4+3
         uint8_t* srow = sb + row * 128;
         if constexpr (OUT_F32) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float4* ptr = reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4));
+          for (int k = 0; k < 4; ++k) {
+            float4* ptr = reinterpret_cast<float4*>(srow + (((half * 4 + k) ^ (row & 7)) << 4));
             float4 q = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             if constexpr (HAS_ADD) {
               const float4 a = *ptr;
@@ -281,32 +292,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {
             float w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float x = v[8 * k + j];
               if constexpr (EPI == EPI_GELU_BF16) x = gelu_erf(x);
               else if constexpr (SPLIT) x = fmaxf(x, 0.f);
-              else if (col0 + 8 * k + j < p.scale_cols) x *= p.col_scale;
+              else if (colh + 8 * k + j < p.scale_cols) x *= p.col_scale;
               w[j] = x;
             }
+            const int seg = ((half * 4 + k) ^ (row & 7)) << 4;
             uint4 q;
             q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
             q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
-            *reinterpret_cast<uint4*>(srow + ((k ^ (row & 7)) << 4)) = q;
+            *reinterpret_cast<uint4*>(srow + seg) = q;
             if constexpr (SPLIT) {
               uint4 l;   // lo = bf16(v - hi)
               l.x = pack_bf16x2(w[0] - __uint_as_float(q.x << 16), w[1] - __uint_as_float(q.x & 0xffff0000u));
               l.y = pack_bf16x2(w[2] - __uint_as_float(q.y << 16), w[3] - __uint_as_float(q.y & 0xffff0000u));
               l.z = pack_bf16x2(w[4] - __uint_as_float(q.z << 16), w[5] - __uint_as_float(q.z & 0xffff0000u));
               l.w = pack_bf16x2(w[6] - __uint_as_float(q.w << 16), w[7] - __uint_as_float(q.w & 0xffff0000u));
-              *reinterpret_cast<uint4*>(srow + GEMM_STG_BYTES + ((k ^ (row & 7)) << 4)) = l;
+              *reinterpret_cast<uint4*>(srow + GEMM_STG_BYTES + seg) = l;
             }
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(2, GEMM_EPI_THREADS);
         if (leader) {
           if constexpr (SPLIT) {
             if (col0 < p.split_part) {
