@@ -55,6 +55,10 @@ constexpr int ATT_BM = 128;     // queries per tile (two tiles per work item)
 constexpr int ATT_BN = 128;     // keys per tile
 constexpr int ATT_DH = 64;      // head dim
 constexpr int ATT_THREADS = 384;
+#ifndef DSG_ATTN_POLY_MASK
+#define DSG_ATTN_POLY_MASK 0x8888
+#endif
+constexpr unsigned ATT_POLY_MASK = DSG_ATTN_POLY_MASK;   // bit i: pair i of every 16-pair chunk uses the polynomial exp2
 constexpr int ATT_TILE_BYTES = 128 * ATT_DH * 2;  // 16 KB (Q, K or V tile)
 
 template <int KV_STAGES>
@@ -327,7 +331,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #ifdef DSG_EXP_NO_MUFU
             const float2 e = x;
 #else
-            const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            // a fixed share of the pairs is evaluated on the FMA/ALU pipes (exp2_poly_x2), the rest on MUFU
+            const float2 e = ((ATT_POLY_MASK >> i) & 1) ? exp2_poly_x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
 #endif
 #ifndef DSG_EXP_NO_SUM
             if (i & 1) sum23 = fadd2(sum23, e); else sum01 = fadd2(sum01, e);

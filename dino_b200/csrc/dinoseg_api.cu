@@ -119,13 +119,15 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 // kernel launchers
 // -----------------------------------------------------------------------------------------
 constexpr int kAttnStages = 4;
+long long* g_attn_timing = nullptr;   // debug: device buffer for DSG_ATTN_TIMING / DSG_GEMM_TIMING builds
 constexpr int kHeadPart = 256;   // width of each bf16x3 part of relu(layer_1) (head_h1 <= 256, zero padded)
 
-template <int EPI>
-cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
-                          const GemmParams& p, int num_sms, cudaStream_t s) {
-  auto kern = gemm_bf16_tn_kernel<EPI>;
-  constexpr size_t smem = gemm_smem_bytes(EPI);
+template <int EPI, bool RES_A>
+cudaError_t launch_gemm_tt(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
+                           const GemmParams& p, int num_sms, cudaStream_t s) {
+  auto kern = gemm_bf16_tn_kernel<EPI, RES_A>;
+  constexpr size_t smem = gemm_smem_bytes(EPI, RES_A);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -137,10 +139,29 @@ cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUte
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int m_tiles = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM * p.batches;
   const long long total = (long long)n_tiles * m_tiles;
-  if (total <= 0 || total > INT32_MAX || p.K % GEMM_BK != 0) return cudaErrorInvalidValue;
-  const int grid = total < num_sms ? int(total) : num_sms;   // persistent: one CTA per SM
-  kern<<<grid, GEMM_THREADS, smem, s>>>(a, w, out, add, p);
+  if (total <= 0 || total > INT32_MAX || p.K % GEMM_BK != 0 || n_tiles * GEMM_BN > GEMM_MAX_N) return cudaErrorInvalidValue;
+  const long long units = RES_A ? m_tiles : total;            // RES_A: CTAs walk whole row blocks
+  const int grid = units < num_sms ? int(units) : num_sms;    // persistent: one CTA per SM
+  GemmParams pp = p;
+  pp.timing = g_attn_timing;
+  kern<<<grid, GEMM_THREADS, smem, s>>>(a, w, out, add, pp);
   return cudaGetLastError();
+}
+
+// The resident-A variant (K <= 384, several n-tiles) halves the L2 -> SM traffic per tile, but on B200 it
+// measured SLOWER than the streaming variant (qkv 0.235 vs 0.200 ms, fc1 0.366 vs 0.339 ms): the single
+// A buffer cannot be refilled early enough for the next row block (gemm.cuh).  It is kept selectable
+// (-DDSG_GEMM_RESA) for the follow-up with a deeper A ring; the default is the streaming variant.
+template <int EPI>
+cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
+                          const GemmParams& p, int num_sms, cudaStream_t s) {
+#ifdef DSG_GEMM_RESA
+  const bool res_a = p.K <= GEMM_RES_KB * GEMM_BK && p.N > GEMM_BN;
+#else
+  const bool res_a = false;
+#endif
+  return res_a ? launch_gemm_tt<EPI, true>(a, w, out, add, p, num_sms, s)
+               : launch_gemm_tt<EPI, false>(a, w, out, add, p, num_sms, s);
 }
 
 cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out,
@@ -156,7 +177,6 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, con
   return cudaErrorInvalidValue;
 }
 
-long long* g_attn_timing = nullptr;   // debug: device buffer for DSG_ATTN_TIMING builds
 
 cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
   p.timing = g_attn_timing;
@@ -900,7 +920,7 @@ int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, 
 }
 
 int dinoseg_debug_set_attn_timing(long long* dev_ptr) {
-#ifdef DSG_ATTN_TIMING
+#if defined(DSG_ATTN_TIMING) || defined(DSG_GEMM_TIMING)
   g_attn_timing = dev_ptr;
   return 0;
 #else

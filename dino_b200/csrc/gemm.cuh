@@ -16,6 +16,10 @@
 //                 -> swizzled shared-memory staging -> TMA store (fully coalesced, tails clipped by
 //                 the tensor map).  Addends (residual stream, positional table) are TMA-loaded into
 //                 the same staging buffers two chunks ahead.
+// RES_A variant (K <= 384): the CTA walks whole 128-row blocks; the A block (all k-blocks, 96 KB) stays
+// resident in shared memory while the CTA sweeps every n-tile of that row block, and is refilled k-block
+// by k-block during the last n-tile.  Only the W tiles stream through the ring: the plain variant re-reads
+// A and W for every tile and is bound by the L2 -> SM bandwidth (~11-13 TB/s measured), not by the MMAs.
 // All global tensors are described by 3-D tensor maps {cols, rows_per_batch, batches}; plain
 // matrices use batches = 1.  The patch-embed GEMM uses batches = frames so that a tile never
 // straddles two frames and its output can skip each frame's cls row (row offset 1).
@@ -43,7 +47,19 @@ struct GemmParams {
   float col_scale;
   int scale_cols;
   int split_part;       // EPI_RELU_SPLIT_BF16: width of each of the three output parts (multiple of 64)
+  long long* timing;    // debug (DSG_GEMM_TIMING builds): [grid][3 roles][8] cycle totals
 };
+
+#ifdef DSG_GEMM_TIMING
+#define GEMM_T(i) do { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } while (0)
+#define GEMM_T_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64()
+#define GEMM_T_DUMP(role) do { if (p.timing) for (int _i = 0; _i < 8; ++_i) \
+    p.timing[(size_t(blockIdx.x) * 3 + (role)) * 8 + _i] = tacc[_i]; } while (0)
+#else
+#define GEMM_T(i) do { } while (0)
+#define GEMM_T_DECL do { } while (0)
+#define GEMM_T_DUMP(role) do { } while (0)
+#endif
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 192;
@@ -63,8 +79,14 @@ __host__ __device__ constexpr int gemm_nbuf(int epi) {
   return (gemm_out_is_f32(epi) || epi == EPI_RELU_SPLIT_BF16) ? 4 : 2;
 }
 __host__ __device__ constexpr int gemm_stages(int epi) { return gemm_nbuf(epi) == 4 ? 3 : 4; }
-__host__ __device__ constexpr size_t gemm_smem_bytes(int epi) {
-  return size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES + size_t(gemm_nbuf(epi)) * GEMM_STG_BYTES + 1024 /*align*/ + 256;
+constexpr int GEMM_MAX_N = 3072;                      // bias vector staged in shared memory
+constexpr int GEMM_BIAS_BYTES = GEMM_MAX_N * 4;
+constexpr int GEMM_RES_KB = 6;                        // resident-A variant: up to 6 k-blocks (K <= 384)
+__host__ __device__ constexpr int gemm_res_wstages(int epi) { return gemm_nbuf(epi) == 4 ? 2 : 3; }
+__host__ __device__ constexpr size_t gemm_smem_bytes(int epi, bool res_a) {
+  return (res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(gemm_res_wstages(epi)) * GEMM_B_BYTES
+                : size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES) +
+         size_t(gemm_nbuf(epi)) * GEMM_STG_BYTES + GEMM_BIAS_BYTES + 1024 /*align*/ + 256;
 }
 
 // GELU with the exact-erf definition (nn.GELU() default, reference vision_transformer.py:50):
@@ -85,7 +107,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x >= 0.f ? fmaf(-x, w, x) : x * w;
 }
 
-template <int EPI>
+template <int EPI, bool RES_A>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
@@ -94,7 +116,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool HAS_ADD = gemm_has_addend(EPI);
   constexpr bool SPLIT = EPI == EPI_RELU_SPLIT_BF16;
   constexpr int BPC = SPLIT ? 2 : 1;             // staging buffers per chunk
-  constexpr int STAGES = gemm_stages(EPI);
+  constexpr int STAGES = RES_A ? gemm_res_wstages(EPI) : gemm_stages(EPI);   // ring depth (W only if RES_A)
+  constexpr int RING_BYTES = RES_A ? GEMM_B_BYTES : GEMM_STAGE_BYTES;
+  constexpr int A_RES_BYTES = RES_A ? GEMM_RES_KB * GEMM_A_BYTES : 0;
   constexpr int NBUF = gemm_nbuf(EPI);
   constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 bytes per row)
   constexpr int NCH = GEMM_BN / CH;
@@ -105,10 +129,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
-  uint8_t* stg = smem + size_t(STAGES) * GEMM_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + size_t(NBUF) * GEMM_STG_BYTES);
+  uint8_t* ring = smem + A_RES_BYTES;            // [A slots (RES_A)] [ring] [staging] [barriers]
+  uint8_t* stg = ring + size_t(STAGES) * RING_BYTES;
+  float* sbias = reinterpret_cast<float*>(stg + size_t(NBUF) * GEMM_STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + size_t(NBUF) * GEMM_STG_BYTES + GEMM_BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full = empty_bar + STAGES;       // 2
+  uint64_t* a_full = empty_bar + STAGES;         // GEMM_RES_KB (RES_A): A k-block landed
+  uint64_t* a_empty = a_full + GEMM_RES_KB;      // GEMM_RES_KB (RES_A): last MMA reading the k-block retired
+  uint64_t* acc_full = a_empty + GEMM_RES_KB;    // 2
   uint64_t* acc_empty = acc_full + 2;            // 2 (8 arrivals: one per epilogue warp)
   uint64_t* add_bar = acc_empty + 2;             // NBUF
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + NBUF);
@@ -121,7 +149,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_kb = p.K / GEMM_BK;
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int m_tiles_pb = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM;
-  const int total_tiles = n_tiles * m_tiles_pb * p.batches;
+  const int m_total = m_tiles_pb * p.batches;
+  const int total_tiles = n_tiles * m_total;
+  // tiles of this CTA: plain = tile ids bid, bid+G, ... (n fastest); RES_A = every n-tile of row blocks bid, bid+G, ...
+  const int my_tiles = RES_A ? (int(blockIdx.x) < m_total ? ((m_total - 1 - int(blockIdx.x)) / int(gridDim.x) + 1) * n_tiles : 0)
+                             : (int(blockIdx.x) < total_tiles ? (total_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0);
+  auto tile_coords = [&](int t, int& mt, int& nt) {
+    if constexpr (RES_A) {
+      mt = int(blockIdx.x) + (t / n_tiles) * int(gridDim.x);
+      nt = t % n_tiles;
+    } else {
+      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      nt = tile % n_tiles;
+      mt = tile / n_tiles;
+    }
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -132,6 +174,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < GEMM_RES_KB; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], GEMM_EPI_THREADS / 32);
@@ -140,6 +186,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  // bias (zero padded to a multiple of the tile width) once per persistent CTA
+  for (int i = threadIdx.x; i < n_tiles * GEMM_BN; i += GEMM_THREADS)
+    sbias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,47 +197,76 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (elect_one()) {
       uint32_t kc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles;
-        const int mt = tile / n_tiles;
+      GEMM_T_DECL;
+      for (int t = 0; t < my_tiles; ++t) {
+        int mt, nt;
+        tile_coords(t, mt, nt);
         const int bt = mt / m_tiles_pb;
         const int r0 = (mt - bt * m_tiles_pb) * GEMM_BM;
+        const int mi = RES_A ? t / n_tiles : 0;    // index of the row block among this CTA's
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          GEMM_T(7);
+          if constexpr (RES_A) {
+            if (nt == 0) {                         // (re)fill the resident A block, k-block by k-block
+              mbar_wait(&a_empty[kb], (mi & 1) ^ 1);
+              mbar_expect_tx(&a_full[kb], GEMM_A_BYTES);
+              tma_load_3d(smem + size_t(kb) * GEMM_A_BYTES, &tmA, &a_full[kb], kb * GEMM_BK, r0, bt);
+            }
+          }
           const int s = kc % STAGES;
+          GEMM_T(0);
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], GEMM_STAGE_BYTES);
-          uint8_t* sa = smem + size_t(s) * GEMM_STAGE_BYTES;
-          tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, r0, bt);
-          tma_load_2d(sa + GEMM_A_BYTES, &tmW, &full_bar[s], kb * GEMM_BK, nt * GEMM_BN);
+          GEMM_T(1);
+          mbar_expect_tx(&full_bar[s], RING_BYTES);
+          uint8_t* sr = ring + size_t(s) * RING_BYTES;
+          if constexpr (!RES_A) tma_load_3d(sr, &tmA, &full_bar[s], kb * GEMM_BK, r0, bt);
+          tma_load_2d(sr + (RES_A ? 0 : GEMM_A_BYTES), &tmW, &full_bar[s], kb * GEMM_BK, nt * GEMM_BN);
+          GEMM_T(2);
         }
       }
+      GEMM_T_DUMP(0);
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN, 0);
       uint32_t kc = 0;
-      int ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      GEMM_T_DECL;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        int mt, nt;
+        tile_coords(ti, mt, nt);
         const int as = ti & 1;
+        GEMM_T(7);
         mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+        GEMM_T(0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as) * ACC_STRIDE;
+        const int mi = RES_A ? ti / n_tiles : 0;
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
           const int s = kc % STAGES;
+          if constexpr (RES_A) {
+            if (nt == 0) mbar_wait(&a_full[kb], mi & 1);
+          }
+          GEMM_T(7);
           mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+          GEMM_T(1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + size_t(s) * GEMM_STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + GEMM_A_BYTES);
+          const uint32_t sr = smem_u32(ring + size_t(s) * RING_BYTES);
+          const uint64_t adesc = umma_desc_sw128(RES_A ? smem_u32(smem + size_t(kb) * GEMM_A_BYTES) : sr);
+          const uint64_t bdesc = umma_desc_sw128(RES_A ? sr : sr + GEMM_A_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >>4 -> +2)
             umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[s]);
+          if constexpr (RES_A) {
+            if (nt == n_tiles - 1) tc_commit(&a_empty[kb]);   // the next row block may overwrite this k-block
+          }
+          GEMM_T(2);
         }
         tc_commit(&acc_full[as]);
       }
+      GEMM_T_DUMP(1);
     }
   } else {
     // ---------------- epilogue: thread <-> accumulator row ----------------
@@ -198,39 +276,46 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool leader = threadIdx.x == 64;
     constexpr int HC = CH / 2;                     // columns per thread per chunk (32 bf16 / 16 fp32 = 64 bytes)
     const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
-    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
     const int total_chunks = my_tiles * NCH;
 
-    // coordinates of this CTA's q-th chunk (q = tile_iter * NCH + c)
-    auto chunk_coords = [&](int q, int& col0, int& r0, int& bt) {
-      const int tile = int(blockIdx.x) + (q / NCH) * int(gridDim.x);
-      const int nt = tile % n_tiles;
-      const int mt = tile / n_tiles;
-      bt = mt / m_tiles_pb;
-      r0 = (mt - bt * m_tiles_pb) * GEMM_BM;
-      col0 = nt * GEMM_BN + (q % NCH) * CH;
+    // coordinates of this CTA's current and next tile (one division per tile, none per chunk)
+    struct TileXY { int col, r0, bt; };
+    auto tile_xy = [&](int t) {
+      int mt, nt;
+      tile_coords(t, mt, nt);
+      TileXY o;
+      o.bt = mt / m_tiles_pb;
+      o.r0 = (mt - o.bt * m_tiles_pb) * GEMM_BM;
+      o.col = nt * GEMM_BN;
+      return o;
     };
-    auto issue_add = [&](int q) {
-      int col0, r0, bt;
-      chunk_coords(q, col0, r0, bt);
+    TileXY cur = tile_xy(0), nxt = tile_xy(1);
+    // addend prefetch for chunk q (= tile q / NCH, chunk q % NCH); q lies in the current or the next tile
+    auto issue_add = [&](int q, int ti_cur) {
+      const int tq = q / NCH;
+      const TileXY& xy = tq == ti_cur ? cur : nxt;
       const int b = q % NBUF;
       mbar_expect_tx(&add_bar[b], GEMM_STG_BYTES);
-      tma_load_3d(stg + size_t(b) * GEMM_STG_BYTES, &tmAdd, &add_bar[b], col0, p.row_off + r0, p.add_batched ? bt : 0);
+      tma_load_3d(stg + size_t(b) * GEMM_STG_BYTES, &tmAdd, &add_bar[b], xy.col + (q - tq * NCH) * CH, p.row_off + xy.r0,
+                  p.add_batched ? xy.bt : 0);
     };
     if (HAS_ADD && leader) {
-      for (int q = 0; q < PD && q < total_chunks; ++q) issue_add(q);
+      for (int q = 0; q < PD && q < total_chunks; ++q) issue_add(q, 0);
     }
 
     int g = 0;                                     // chunk counter of this CTA
+    GEMM_T_DECL;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int as = ti & 1;
+      if (ti > 0) { cur = nxt; nxt = tile_xy(ti + 1); }
+      GEMM_T(7);
       mbar_wait(&acc_full[as], (ti >> 1) & 1);
+      GEMM_T(0);
       tc_fence_after();
       const uint32_t acc = lane_base + uint32_t(as) * ACC_STRIDE;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++g) {
-        int col0, r0, bt;
-        chunk_coords(g, col0, r0, bt);
+        const int col0 = cur.col + c * CH, r0 = cur.r0, bt = cur.bt;
         const int b = (g * BPC) % NBUF;
         uint8_t* sb = stg + size_t(b) * GEMM_STG_BYTES;
         const int colh = col0 + half * HC;         // first global column of this thread's segment
@@ -249,31 +334,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         }
         tmem_ld_wait();
+        GEMM_T(1);
         if (c == NCH - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);   // the MMA warp may start tile ti+2 in this stage
         }
-        if (p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < HC; i += 4) {
-            if (colh + i < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + colh + i));
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
-          }
+        for (int i = 0; i < HC; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + colh + i);   // smem broadcast
+          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
         }
         // staging buffer b: the TMA store that last read it (chunk g - NBUF) must be done, and for
         // addend epilogues the prefetch of chunk g + PD goes into the buffer of chunk g + PD - NBUF
+        GEMM_T(2);
         if (leader) {
           tma_store_wait_read<NBUF / BPC - PD - 1>();
-          if (HAS_ADD && g + PD < total_chunks) issue_add(g + PD);
+          if (HAS_ADD && g + PD < total_chunks) issue_add(g + PD, ti);
         }
+        GEMM_T(3);
         if constexpr (HAS_ADD) {
           mbar_wait(&add_bar[b], (g / NBUF) & 1);
         } else {
           named_bar_sync(1, GEMM_EPI_THREADS);
         }
+        GEMM_T(4);
         // 128-byte staging row = 8 x 16-byte segments, XOR-swizzled with the row index (SWIZZLE_128B);
         // this thread owns segments half*4 .. half*4+3
         uint8_t* srow = sb + row * 128;
@@ -317,8 +402,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        GEMM_T(5);
         fence_proxy_async_smem();
         named_bar_sync(2, GEMM_EPI_THREADS);
+        GEMM_T(6);
         if (leader) {
           if constexpr (SPLIT) {
             if (col0 < p.split_part) {
@@ -333,6 +420,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    if (leader) { GEMM_T_DUMP(2); }
     if (leader) tma_store_wait<0>();               // all output bytes are globally visible before exit
   }
 
