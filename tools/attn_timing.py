@@ -27,15 +27,21 @@ def main():
     timing = torch.zeros(148 * 3 * 8, dtype=torch.int64, device="cuda")
     lib.dinoseg_debug_set_attn_timing.argtypes = [C.c_void_p]
     lib.dinoseg_op_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    assert lib.dinoseg_debug_set_attn_timing(timing.data_ptr()) == 0
-    for _ in range(2):
+    have_timing = lib.dinoseg_debug_set_attn_timing(timing.data_ptr()) == 0
+    for _ in range(3):
         lib.dinoseg_op_attention(qkv.data_ptr(), out.data_ptr(), B, N, H, None)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 1 if have_timing else 10
     e0.record()
-    lib.dinoseg_op_attention(qkv.data_ptr(), out.data_ptr(), B, N, H, None)
+    for _ in range(reps):
+        lib.dinoseg_op_attention(qkv.data_ptr(), out.data_ptr(), B, N, H, None)
     e1.record()
     torch.cuda.synchronize()
+    if not have_timing:
+        ms = e0.elapsed_time(e1) / reps
+        print(f"kernel {ms:.3f} ms  ({4.0 * B * N * N * D / ms / 1e9:.0f} TFLOP/s)")
+        return
     tm = timing[148 * 16:].view(148, 8).double().cpu().mean(0)
     t = timing[:148 * 16].view(148, 2, 8).double().cpu()
     qpairs = (N + 255) // 256

@@ -87,6 +87,105 @@ __global__ void softmax_body_kernel(float* out, long long* cycles, float seed, i
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// softmax body variant 2: optional tcgen05.st of the packed probabilities and polynomial exp2 share
+__device__ __forceinline__ float2 ub_ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 ub_fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 ub_poly(float2 x) {
+  x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+  const float2 t = ub_fadd2(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = ub_fadd2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ub_ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 p = ub_ffma2(make_float2(0.0550886f, 0.0550886f), f, make_float2(0.242604f, 0.242604f));
+  p = ub_ffma2(p, f, make_float2(0.693276f, 0.693276f));
+  p = ub_ffma2(p, f, make_float2(0.999929f, 0.999929f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+template <unsigned POLY, bool DO_ST>
+__global__ void softmax_body2_kernel(float* out, long long* cycles, float seed) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 32;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = seed * (threadIdx.x + i) * 1e-3f - 1.0f;
+  float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
+  const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+  const float2 nmb = make_float2(-seed, -seed);
+  __syncthreads();
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS / 4; ++it) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 x = ub_ffma2(make_float2(v[2 * i], v[2 * i + 1]), l2e, nmb);
+      float2 e;
+      if ((POLY >> i) & 1) e = ub_poly(x);
+      else {
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+      }
+      if (i & 1) sum23 = ub_fadd2(sum23, e); else sum01 = ub_fadd2(sum01, e);
+      asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(e.y), "f"(e.x));
+      v[2 * i] = e.x - 1.5f;
+    }
+    if (DO_ST) {
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+          "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(base + (it & 1) * 16),
+          "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]),
+          "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]) : "memory");
+    } else {
+      v[1] += __uint_as_float(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]) * 1e-30f;
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum01.x + sum01.y + sum23.x + sum23.y + v[1];
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(slot) : "memory");
+}
+
+template <unsigned POLY, bool DO_ST>
+void run_body2(const char* name) {
+  for (int w : {4, 8, 16}) {
+    int nsm = 148;
+    float* out; long long* cyc;
+    cudaMalloc(&out, sizeof(float) * nsm * w * 32);
+    cudaMalloc(&cyc, sizeof(long long) * nsm);
+    softmax_body2_kernel<POLY, DO_ST><<<nsm, w * 32>>>(out, cyc, 0.37f);
+    cudaDeviceSynchronize();
+    softmax_body2_kernel<POLY, DO_ST><<<nsm, w * 32>>>(out, cyc, 0.37f);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(nsm);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost);
+    std::sort(h.begin(), h.end());
+    double elems = double(w) * 32 * (ITERS / 4) * 32;
+    printf("%-44s warps=%2d: %.2f exps/clk/SM (%s)\n", name, w, elems / double(h[nsm / 2]), cudaGetErrorString(e));
+    cudaFree(out); cudaFree(cyc);
+  }
+}
+
 // tcgen05.ld throughput: W warps (W multiple of 4) each repeatedly load 32 lanes x 32 columns
 __global__ void tmem_ld_kernel(float* out, long long* cycles, int reps, int x64) {
   __shared__ uint32_t slot;
@@ -164,6 +263,11 @@ int main() {
     run<10>("add.f16x2", w, 2);
     run<11>("fma.f32x2", w, 2);
   }
+  run_body2<0x0000, false>("body2: all MUFU, no st");
+  run_body2<0x0000, true>("body2: all MUFU, tcgen05.st");
+  run_body2<0x8888, false>("body2: 25% poly, no st");
+  run_body2<0x8888, true>("body2: 25% poly, tcgen05.st");
+  run_body2<0xAAAA, true>("body2: 50% poly, tcgen05.st");
   for (int w : {4, 8, 12, 16}) {
     int nsm = 148;
     float* out; long long* cyc;
