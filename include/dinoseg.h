@@ -77,11 +77,11 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
  * device, runs dinoseg_forward, copies the label maps back and SYNCHRONISES the stream.
  * This is the call that replaces a loop of DINOSeg.predict() (pl_torch_modules.py:276-300)
  * after preprocessing.  host_lowres / host_labels may be NULL individually.  Internally the batch is
- * pipelined in chunks over two library-owned streams and staging buffers. */
+ * pipelined in chunks over three library-owned streams and staging buffers. */
 int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
                          int64_t* host_labels, void* stream);
 
-/* Frames per pipeline chunk of dinoseg_predict_host (default 16): the host batch is processed in chunks
+/* Frames per pipeline chunk of dinoseg_predict_host (default 8): the host batch is processed in chunks
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 
