@@ -19,6 +19,7 @@
 #include "attention.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "mlp.cuh"
 
 using namespace dsg;
 
@@ -119,7 +120,26 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 // kernel launchers
 // -----------------------------------------------------------------------------------------
 constexpr int kAttnStages = 4;
-long long* g_attn_timing = nullptr;   // debug: device buffer for DSG_ATTN_TIMING / DSG_GEMM_TIMING builds
+long long* g_attn_timing = nullptr;   // debug: device buffer for the DSG_*_TIMING builds
+
+cudaError_t launch_mlp_fused(const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& x, const MlpParams& p,
+                             int num_sms, cudaStream_t s) {
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MLP_SMEM));
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  const int m_blocks = (p.M + MLP_BM - 1) / MLP_BM;
+  const int grid = m_blocks < num_sms ? m_blocks : num_sms;
+  MlpParams pp = p;
+  pp.timing = g_attn_timing;
+  mlp_fused_kernel<<<grid, MLP_THREADS, MLP_SMEM, s>>>(w1, w2, x, pp);
+  return cudaGetLastError();
+}
+
 constexpr int kHeadPart = 256;   // width of each bf16x3 part of relu(layer_1) (head_h1 <= 256, zero padded)
 
 template <int EPI, bool RES_A>
@@ -245,6 +265,7 @@ struct BlockW {
   __nv_bfloat16 *qkv_w = nullptr, *proj_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
   float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
   CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+  CUtensorMap tm_fc1_g, tm_fc2_g;   // 128-row granule views for the fused MLP kernel
 };
 
 struct WeightSlot {
@@ -314,6 +335,7 @@ struct dinoseg {
 
   int debug_stop = 0;
   int launches = 0;
+  bool fused_mlp = false;           // D = 384 / hidden = 1536: fused LN2 -> fc1 -> GELU -> fc2 kernel
 
   // optional per-kernel-kind timing (cudaEvents around every launch of a forward)
   bool profile = false;
@@ -410,9 +432,10 @@ int bind_workspace(dinoseg* h, WorkBufs& w, void* ws, size_t ws_bytes, int batch
 
 namespace {
 enum Kind { K_IM2COL = 0, K_CLS, K_GEMM_PATCH, K_LN, K_GEMM_QKV, K_ATTN, K_GEMM_PROJ, K_GEMM_FC1, K_GEMM_FC2,
-            K_GEMM_HEAD, K_HEAD_TAIL, K_REPLICATE, K_COUNT };
+            K_GEMM_HEAD, K_HEAD_TAIL, K_REPLICATE, K_MLP_FUSED, K_COUNT };
 const char* const kKindNames[K_COUNT] = {"im2col", "cls_row", "gemm_patch", "layernorm", "gemm_qkv", "attention",
-                                         "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_head", "head_tail", "replicate"};
+                                         "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_head", "head_tail", "replicate",
+                                         "mlp_fused"};
 
 // RAII pair of events around one launch (no-op unless profiling is on)
 struct LaunchScope {
@@ -467,6 +490,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   dinoseg* h = new dinoseg();
   h->cfg = *cfg;
   h->device = device;
+  h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
   h->num_sms = prop.multiProcessorCount;
   const int D = cfg->embed_dim, HID = cfg->mlp_hidden, G0 = cfg->pos_grid, C = cfg->n_classes;
   const int H1 = cfg->head_h1, H2 = cfg->head_h2;
@@ -517,6 +541,8 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc1, b.fc1_w, HID, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, GEMM_BN);
+    ok &= make_tmap_2d(&b.tm_fc1_g, b.fc1_w, HID, D, D, 128);
+    ok &= make_tmap_2d(&b.tm_fc2_g, b.fc2_w, D, HID, HID, 128);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed for block weights"; rc = -1; }
   }
   if (rc == 0) {
@@ -734,16 +760,24 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, int batc
       DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_abuf, b.tm_proj, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
     }
     if (stop == 3 + 3 * i) { h->launches = n; return 0; }
-    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
-    {
-      GemmParams p = gp(HID, D, b.fc1_b);
-      LaunchScope ls(h, K_GEMM_FC1, s);
-      DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, w.tm_abuf, b.tm_fc1, w.tm_hid_out, w.tm_hid_out, p, sms, s)); ++n;
-    }
-    {
-      GemmParams p = gp(D, HID, b.fc2_b);
-      LaunchScope ls(h, K_GEMM_FC2, s);
-      DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_hid, b.tm_fc2, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
+    if (h->fused_mlp) {
+      // LayerNorm2 -> fc1 -> GELU -> fc2 -> +x in ONE kernel (ViT-S: D = 384, hidden = 1536)
+      MlpParams p{};
+      p.M = M; p.x = w.x; p.ln_g = b.ln2_g; p.ln_b = b.ln2_b; p.b1 = b.fc1_b; p.b2 = b.fc2_b; p.eps = eps;
+      LaunchScope ls(h, K_MLP_FUSED, s);
+      DSG_CUDA(h, launch_mlp_fused(b.tm_fc1_g, b.tm_fc2_g, w.tm_x_out, p, sms, s)); ++n;
+    } else {
+      { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
+      {
+        GemmParams p = gp(HID, D, b.fc1_b);
+        LaunchScope ls(h, K_GEMM_FC1, s);
+        DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, w.tm_abuf, b.tm_fc1, w.tm_hid_out, w.tm_hid_out, p, sms, s)); ++n;
+      }
+      {
+        GemmParams p = gp(D, HID, b.fc2_b);
+        LaunchScope ls(h, K_GEMM_FC2, s);
+        DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_hid, b.tm_fc2, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
+      }
     }
     if (stop == 4 + 3 * i) { h->launches = n; return 0; }
   }
@@ -920,13 +954,37 @@ int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, 
 }
 
 int dinoseg_debug_set_attn_timing(long long* dev_ptr) {
-#if defined(DSG_ATTN_TIMING) || defined(DSG_GEMM_TIMING)
+#if defined(DSG_ATTN_TIMING) || defined(DSG_GEMM_TIMING) || defined(DSG_MLP_TIMING)
   g_attn_timing = dev_ptr;
   return 0;
 #else
   (void)dev_ptr;
   return -1;   // the library was not built with -DDSG_ATTN_TIMING
 #endif
+}
+
+int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
+  if (!h) return -1;
+  if (on && !(h->cfg.embed_dim == MLP_D && h->cfg.mlp_hidden == MLP_HID))
+    DSG_FAIL(h, "the fused MLP kernel needs embed_dim 384 and mlp_hidden 1536");
+  h->fused_mlp = on != 0;
+  return 0;
+}
+
+int dinoseg_op_mlp(float* x, const float* ln_g, const float* ln_b, const void* W1_bf16, const float* b1,
+                   const void* W2_bf16, const float* b2, int M, float eps, void* stream) {
+  if (!x || !ln_g || !ln_b || !W1_bf16 || !b1 || !W2_bf16 || !b2 || M <= 0) return -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap t1, t2, tx;
+  bool ok = make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, 128);
+  ok &= make_tmap_2d(&t2, W2_bf16, MLP_D, MLP_HID, MLP_HID, 128);
+  ok &= make_tmap_gemm_out(&tx, x, true, MLP_D, M, 1, MLP_D);
+  if (!ok) return -2;
+  MlpParams p{};
+  p.M = M; p.x = x; p.ln_g = ln_g; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2; p.eps = eps;
+  return launch_mlp_fused(t1, t2, tx, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {

@@ -121,6 +121,34 @@ def check_attention(name, B, N, H):
                    ref_absmax=scale, tol=tol, n_bad=int(bad.shape[0]), first_bad=first_bad)
 
 
+def check_mlp(name, M):
+    """Fused LN -> fc1 -> GELU(erf) -> fc2 -> +x kernel vs fp32 torch (bf16 operand rounding emulated for the
+    reference's inputs only through the tolerance: 1 % of the output's max-abs)."""
+    torch, L, lib = _imports()
+    torch.manual_seed(7)
+    dev = "cuda"
+    x = torch.randn(M, 384, device=dev) * 1.5 + 0.2
+    g = 1.0 + 0.1 * torch.randn(384, device=dev)
+    b = 0.1 * torch.randn(384, device=dev)
+    W1 = (torch.randn(1536, 384, device=dev) * 0.05).to(torch.bfloat16)
+    b1 = 0.1 * torch.randn(1536, device=dev)
+    W2 = (torch.randn(384, 1536, device=dev) * 0.03).to(torch.bfloat16)
+    b2 = 0.1 * torch.randn(384, device=dev)
+    F = torch.nn.functional
+    ln = F.layer_norm(x, (384,), g, b, 1e-6)
+    hid = F.gelu(F.linear(ln.to(torch.bfloat16).float(), W1.float(), b1))
+    ref = x + F.linear(hid.to(torch.bfloat16).float(), W2.float(), b2)
+    y = x.clone()
+    rc = lib.dinoseg_op_mlp(_ptr(y), _ptr(g), _ptr(b), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, 1e-6, None)
+    torch.cuda.synchronize()
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    tol = 1e-2 * scale
+    bad = ((y - ref).abs() > tol).nonzero()
+    return _report(name, rc == 0 and err <= tol and bool(torch.isfinite(y).all()), rc=rc, max_abs_err=err,
+                   ref_absmax=scale, tol=tol, n_bad=int(bad.shape[0]), first_bad=bad[0].tolist() if bad.numel() else None)
+
+
 def check_layernorm(name, M, D):
     torch, L, lib = _imports()
     torch.manual_seed(3)
@@ -221,6 +249,9 @@ def _checks():
         "attn_901": lambda: check_attention("attn_901", 2, 901, 6),
         "attn_3601": lambda: check_attention("attn_3601", 1, 3601, 6),
         "attn_vitb_901": lambda: check_attention("attn_vitb_901", 1, 901, 12),
+        "mlp_1block": lambda: check_mlp("mlp_1block", 128),
+        "mlp_ragged": lambda: check_mlp("mlp_ragged", 901),
+        "mlp_multi": lambda: check_mlp("mlp_multi", 148 * 128 * 2 + 77),
     }
 
 
@@ -229,7 +260,7 @@ def check_names():
         "layernorm_384", "layernorm_768", "posembed_30", "posembed_60", "posembed_28", "posembed_vitb_60", "im2col",
         "argmax_replicate", "argmax_replicate_odd", "gemm_tile", "gemm_k384", "gemm_qkv", "gemm_gelu",
         "gemm_resid_k1536", "gemm_patch", "gemm_head", "gemm_big", "attn_1tile", "attn_ragged_small", "attn_2tiles",
-        "attn_901", "attn_3601", "attn_vitb_901",
+        "attn_901", "attn_3601", "attn_vitb_901", "mlp_1block", "mlp_ragged", "mlp_multi",
     ]
 
 
