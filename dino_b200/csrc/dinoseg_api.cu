@@ -122,7 +122,7 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 constexpr int kAttnStages = 4;
 long long* g_attn_timing = nullptr;   // debug: device buffer for the DSG_*_TIMING builds
 
-cudaError_t launch_mlp_fused(const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& x, const MlpParams& p,
+cudaError_t launch_mlp_fused(const CUtensorMap& a, const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& x, const MlpParams& p,
                              int num_sms, cudaStream_t s) {
   static bool attr[64] = {};
   int dev = 0;
@@ -136,7 +136,7 @@ cudaError_t launch_mlp_fused(const CUtensorMap& w1, const CUtensorMap& w2, const
   const int grid = m_blocks < num_sms ? m_blocks : num_sms;
   MlpParams pp = p;
   pp.timing = g_attn_timing;
-  mlp_fused_kernel<<<grid, MLP_THREADS, MLP_SMEM, s>>>(w1, w2, x, pp);
+  mlp_fused_kernel<<<grid, MLP_THREADS, MLP_SMEM, s>>>(a, w1, w2, x, pp);
   return cudaGetLastError();
 }
 
@@ -761,11 +761,12 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, int batc
     }
     if (stop == 3 + 3 * i) { h->launches = n; return 0; }
     if (h->fused_mlp) {
-      // LayerNorm2 -> fc1 -> GELU -> fc2 -> +x in ONE kernel (ViT-S: D = 384, hidden = 1536)
+      // LayerNorm2, then fc1 -> GELU -> fc2 -> +x in ONE kernel (ViT-S: D = 384, hidden = 1536)
+      { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
       MlpParams p{};
-      p.M = M; p.x = w.x; p.ln_g = b.ln2_g; p.ln_b = b.ln2_b; p.b1 = b.fc1_b; p.b2 = b.fc2_b; p.eps = eps;
+      p.M = M; p.x = w.x; p.b1 = b.fc1_b; p.b2 = b.fc2_b;
       LaunchScope ls(h, K_MLP_FUSED, s);
-      DSG_CUDA(h, launch_mlp_fused(b.tm_fc1_g, b.tm_fc2_g, w.tm_x_out, p, sms, s)); ++n;
+      DSG_CUDA(h, launch_mlp_fused(w.tm_abuf, b.tm_fc1_g, b.tm_fc2_g, w.tm_x_out, p, sms, s)); ++n;
     } else {
       { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
       {
@@ -971,20 +972,21 @@ int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
   return 0;
 }
 
-int dinoseg_op_mlp(float* x, const float* ln_g, const float* ln_b, const void* W1_bf16, const float* b1,
-                   const void* W2_bf16, const float* b2, int M, float eps, void* stream) {
-  if (!x || !ln_g || !ln_b || !W1_bf16 || !b1 || !W2_bf16 || !b2 || M <= 0) return -1;
+int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                   const float* b2, int M, void* stream) {
+  if (!x || !A_bf16 || !W1_bf16 || !b1 || !W2_bf16 || !b2 || M <= 0) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  CUtensorMap t1, t2, tx;
-  bool ok = make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, 128);
+  CUtensorMap ta, t1, t2, tx;
+  bool ok = make_tmap_gemm_a(&ta, A_bf16, M, 1, MLP_D);
+  ok &= make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, 128);
   ok &= make_tmap_2d(&t2, W2_bf16, MLP_D, MLP_HID, MLP_HID, 128);
   ok &= make_tmap_gemm_out(&tx, x, true, MLP_D, M, 1, MLP_D);
   if (!ok) return -2;
   MlpParams p{};
-  p.M = M; p.x = x; p.ln_g = ln_g; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2; p.eps = eps;
-  return launch_mlp_fused(t1, t2, tx, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+  p.M = M; p.x = x; p.b1 = b1; p.b2 = b2;
+  return launch_mlp_fused(ta, t1, t2, tx, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {

@@ -122,10 +122,10 @@ int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int
 /* Debug builds only (-DDSG_ATTN_TIMING): device buffer [grid][2][8] of int64 receiving the per-phase
  * cycle totals of the attention kernel's softmax warpgroups; returns -1 in regular builds. */
 int dinoseg_debug_set_attn_timing(long long* dev_ptr);
-/* x[M,384] fp32 (in place) += fc2(gelu(fc1(LayerNorm(x)))) with W1 [1536,384], W2 [384,1536] bf16: the fused
- * transformer-MLP kernel (reference vision_transformer.py:135 with :118, :59-65) */
-int dinoseg_op_mlp(float* x, const float* ln_g, const float* ln_b, const void* W1_bf16, const float* b1,
-                   const void* W2_bf16, const float* b2, int M, float eps, void* stream);
+/* x[M,384] fp32 (in place) += fc2(gelu(fc1(A))) with A [M,384] bf16 (= LayerNorm2(x)), W1 [1536,384], W2 [384,1536]
+ * bf16: the fused transformer-MLP kernel (reference vision_transformer.py:135, :59-65) */
+int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                   const float* b2, int M, void* stream);
 /* switch between the fused MLP kernel (default for ViT-S) and the unfused LN / fc1 / fc2 kernels */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,

@@ -122,7 +122,7 @@ def check_attention(name, B, N, H):
 
 
 def check_mlp(name, M):
-    """Fused LN -> fc1 -> GELU(erf) -> fc2 -> +x kernel vs fp32 torch (bf16 operand rounding emulated for the
+    """Fused fc1 -> GELU(erf) -> fc2 -> +x kernel (A = LayerNorm(x) in bf16) vs fp32 torch (bf16 operand rounding emulated for the
     reference's inputs only through the tolerance: 1 % of the output's max-abs)."""
     torch, L, lib = _imports()
     torch.manual_seed(7)
@@ -139,7 +139,8 @@ def check_mlp(name, M):
     hid = F.gelu(F.linear(ln.to(torch.bfloat16).float(), W1.float(), b1))
     ref = x + F.linear(hid.to(torch.bfloat16).float(), W2.float(), b2)
     y = x.clone()
-    rc = lib.dinoseg_op_mlp(_ptr(y), _ptr(g), _ptr(b), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, 1e-6, None)
+    A = ln.to(torch.bfloat16).contiguous()
+    rc = lib.dinoseg_op_mlp(_ptr(y), _ptr(A), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, None)
     torch.cuda.synchronize()
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()

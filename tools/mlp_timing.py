@@ -10,13 +10,13 @@ import torch  # noqa: E402
 
 so = os.environ.get("DSG_TIMING_SO", os.path.join(ROOT, "tools", "ubench", "libdinoseg_mtiming.so"))
 MMA = ["wait w_full", "wait acc1_empty", "wait g_full", "wait a_full", "wait acc2_empty", "-", "-", "issue + other"]
-EPI = ["LN prologue", "wait acc1_full", "ld + gelu", "wait g_empty", "write G", "wait acc2_full", "final epilogue", "other"]
+EPI = ["-", "wait acc1_full", "ld + gelu", "wait g_empty", "write G", "-", "-", "other"]
 
 
 def main():
     lib = C.CDLL(so)
     lib.dinoseg_debug_set_attn_timing.argtypes = [C.c_void_p]
-    lib.dinoseg_op_mlp.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_float, C.c_void_p]
+    lib.dinoseg_op_mlp.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
     M = 64 * 3601
     dev = "cuda"
     x = torch.randn(M, 384, device=dev)
@@ -25,7 +25,8 @@ def main():
     W2 = (torch.randn(384, 1536, device=dev) * 0.03).to(torch.bfloat16); b2 = torch.zeros(384, device=dev)
     timing = torch.zeros(148 * 2 * 8, dtype=torch.int64, device=dev)
     have = lib.dinoseg_debug_set_attn_timing(timing.data_ptr()) == 0
-    args = (x.data_ptr(), g.data_ptr(), b.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, 1e-6, None)
+    A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
+    args = (x.data_ptr(), A.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, None)
     for _ in range(2):
         lib.dinoseg_op_mlp(*args)
     torch.cuda.synchronize()
@@ -42,7 +43,7 @@ def main():
     if have:
         t = timing.view(148, 2, 8).double().cpu().mean(0)
         for role, names in ((0, MMA), (1, EPI)):
-            print("  " + ["mma", "epilogue(leader)"][role] + ": " +
+            print("  " + ["mma", "gelu warp 2"][role] + ": " +
                   ", ".join(f"{n}={t[role][i].item() / blocks:.0f}" for i, n in enumerate(names) if n != "-"))
 
 
