@@ -281,7 +281,7 @@ def main():
                "h2d_bytes_per_step": int(frames_host.numel() * 4 * world),
                "d2h_bytes_per_step": int(out.size * 8 * world),
                "api": "DINOSeg.predict_batch(pinned host fp32 frames) -> int64 host label maps (dinoseg_predict_host: "
-                      "H2D + forward + D2H + sync inside the timed region, pipelined over 8-frame chunks on 3 streams)"}
+                      "H2D + forward + D2H + sync inside the timed region, pipelined over ~10-frame chunks on 3 streams)"}
     t_wall2 = time.time()
     clocks = None
     if rank == 0:
@@ -308,7 +308,12 @@ def main():
     if att_n:
         ach = f_launch / (att_ms / att_n * 1e-3) / 1e12
         roofline = {"kernel": "attn_fwd_kernel (fused QK^T -> softmax -> PV, tcgen05/TMEM)", "bound": "tensor",
-                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+                    # exact workload (profiles/r01_attn_ncu_full.csv): 531.1 MB + 158.0 MB; algorithmic = 531 MB of
+                    # q/k/v read once + 177 MB of output
+                    "traffic": 689.2e6 if (B, res, args.arch) == (64, 480, "vit_small") else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r01_attn_ncu_full.csv)",
                     "peak_source": peaks_src + ", sustained figure (kernel timed inside a long step)",
                     "flops_per_launch": f_launch, "launches_timed": att_n, "avg_launch_ms": att_ms / att_n,
                     "share_of_step": att_ms / ms}
@@ -329,7 +334,7 @@ def main():
     }
     if kinds is not None:
         out["kernels"] = kinds
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # N = 1 only (bench contract)
         out["cpu_baseline"] = cpu_baseline(args, sd, cfg)
     if rank == 0:
         print(json.dumps(out), flush=True)

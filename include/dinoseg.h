@@ -81,7 +81,7 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
 int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
                          int64_t* host_labels, void* stream);
 
-/* Frames per pipeline chunk of dinoseg_predict_host (default 8): the host batch is processed in chunks
+/* Frames per pipeline chunk of dinoseg_predict_host (0 = automatic, the default): the host batch is processed in chunks
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 
