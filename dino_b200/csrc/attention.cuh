@@ -17,14 +17,14 @@
 //
 // Warp roles (384 threads, 1 CTA/SM, all 512 TMEM columns):
 //   warp 0      : TMA producer (Q pair per item; K,V ring)
-//   warp 1      : TMEM alloc + single-thread tcgen05.mma issuer
+//   warps 1, 2  : one tcgen05.mma-issuing thread per query tile (warp 1 also allocates TMEM)
 //                   S_t = Q_t K^T          (SS, both K-major)            t = 0,1
 //                   O_t += P_t V           (TS: P from TMEM, V MN-major: V is never transposed)
 //                 S_t, P_t and O_t have their OWN TMEM columns (2x128 + 2x64 + 2x64 = 512), so
 //                 QK_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers
 //                 (s_empty), long before P_t(j) exists: the softmax warps never wait for the tensor
 //                 pipe.  Issue order per key tile j:  QK0(j+1) QK1(j+1) PV0(j) PV1(j).
-//   warps 2,3   : idle (they only complete the producer warpgroup for setmaxnreg)
+//   warp 3      : idle (it only completes the producer warpgroup for setmaxnreg)
 //   warps 4..7  : softmax of query tile 0, one query row per thread (tcgen05.ld 32x32b)
 //   warps 8..11 : softmax of query tile 1
 // The exponentials are the bottleneck at head_dim 64 (16 MUFU.EX2 per clock per SM vs 8192 tensor
@@ -107,10 +107,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    mbar_init(q_empty, 2);                       // one commit per MMA issuer
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
@@ -151,46 +151,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           tma_load_3d(sk + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.D + h * ATT_DH, j * ATT_BN, b);
         }
       }
-    } else if (warp == 1 && elect_one()) {
-      // ------------------------------ MMA issuer ------------------------------
+    } else if ((warp == 1 || warp == 2) && elect_one()) {
+      // ------------------------------ MMA issuers ------------------------------
+      // one issuing thread per query tile (warp 1: tile 0, warp 2: tile 1): with a single in-order issuer the
+      // PV of one tile waits behind barrier waits that belong to the other tile
+      const int t = warp - 1;
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0);  // K^T: K-major B
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_DH, 1);  // V  : MN-major B
-      const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t qdesc1 = umma_desc_sw128(smem_u32(sQ + ATT_TILE_BYTES));
-      uint32_t kvc = 0, c0 = 0, c1 = 0;   // c_t: key tiles of query tile t processed so far (barrier phases)
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + size_t(t) * ATT_TILE_BYTES));
+      const uint32_t s_tmem = tmem_base + S_COL0 + uint32_t(t * 128);
+      const uint32_t p_tmem = tmem_base + P_COL0 + uint32_t(t * 64);
+      const uint32_t o_tmem = tmem_base + O_COL0 + uint32_t(t * 64);
+      uint32_t kvc = 0, ct = 0;           // ct: key tiles of this query tile processed so far (barrier phases)
       int it = 0;
 #ifdef DSG_ATTN_TIMING
       long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tprev = clock64();
 #endif
-      auto issue_qk = [&](int t, uint32_t kv_counter) {
+      auto issue_qk = [&](uint32_t kv_counter) {
         const uint32_t sk = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES);
         const uint64_t kdesc = umma_desc_sw128(sk);
-        const uint64_t qdesc = t ? qdesc1 : qdesc0;
 #pragma unroll
         for (int k = 0; k < ATT_DH / 16; ++k)
-          umma_ss(tmem_base + S_COL0 + uint32_t(t * 128), qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk,
-                  k != 0);
+          umma_ss(s_tmem, qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk, k != 0);
         tc_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, uint32_t kv_counter, bool accumulate) {
+      auto issue_pv = [&](uint32_t kv_counter, bool accumulate) {
         const uint32_t sv = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
         const uint64_t vdesc = umma_desc_sw128(sv);
         // P: 8 TMEM columns (16 bf16 keys) per K step; V: 16 keys = 2 KB per K step
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(tmem_base + O_COL0 + uint32_t(t * 64), tmem_base + P_COL0 + uint32_t(t * 64 + k * 8),
-                  vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+          umma_ts(o_tmem, p_tmem + uint32_t(k * 8), vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
         tc_commit(&pv_done[t]);
       };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int qp = item % p.qpairs;
-        const bool two = qp * 2 * ATT_BM + ATT_BM < p.N;
+        const bool active = qp * 2 * ATT_BM + t * ATT_BM < p.N;   // tile 1 of the last pair may be empty
         mbar_wait(q_full, it & 1);
         mbar_wait(&kv_full[kvc % KV_STAGES], (kvc / KV_STAGES) & 1);
         tc_fence_after();
-        issue_qk(0, kvc);
-        if (two) issue_qk(1, kvc);
+        if (active) issue_qk(kvc);
         if (num_tiles == 1) tc_commit(q_empty);
         for (int j = 0; j < num_tiles; ++j, ++kvc) {
           const bool more = j + 1 < num_tiles;
@@ -199,38 +200,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
             ATT_T(7);
             mbar_wait(&kv_full[(kvc + 1) % KV_STAGES], ((kvc + 1) / KV_STAGES) & 1);
             ATT_T(0);
-            mbar_wait(&s_empty[0], c0 & 1);
-            ATT_T(1);
-            tc_fence_after();
-            issue_qk(0, kvc + 1);
-            ATT_T(6);
-            if (two) {
-              mbar_wait(&s_empty[1], c1 & 1);
-              ATT_T(2);
+            if (active) {
+              mbar_wait(&s_empty[t], ct & 1);
+              ATT_T(1);
               tc_fence_after();
-              issue_qk(1, kvc + 1);
+              issue_qk(kvc + 1);
               ATT_T(6);
             }
-            if (j + 2 == num_tiles) tc_commit(q_empty);  // last reads of Q0/Q1 have been issued
+            if (j + 2 == num_tiles) tc_commit(q_empty);  // this tile's last read of Q has been issued
           }
-          ATT_T(7);
-          mbar_wait(&p_full[0], c0 & 1); ++c0;
-          ATT_T(3);
-          tc_fence_after();
-          issue_pv(0, kvc, j != 0);
-          ATT_T(6);
-          if (two) {
-            mbar_wait(&p_full[1], c1 & 1); ++c1;
-            ATT_T(4);
+          if (active) {
+            ATT_T(7);
+            mbar_wait(&p_full[t], ct & 1); ++ct;
+            ATT_T(3);
             tc_fence_after();
-            issue_pv(1, kvc, j != 0);
+            issue_pv(kvc, j != 0);
             ATT_T(6);
           }
-          tc_commit(&kv_empty[kvc % KV_STAGES]);      // K(j), V(j) fully consumed once these MMAs retire
+          tc_commit(&kv_empty[kvc % KV_STAGES]);      // this tile's reads of K(j), V(j) have been issued
         }
       }
 #ifdef DSG_ATTN_TIMING
-      if (p.timing != nullptr)
+      if (p.timing != nullptr && t == 0)
         for (int i = 0; i < 8; ++i) p.timing[(size_t(gridDim.x) * 2 + blockIdx.x) * 8 + i] = tacc[i];
 #endif
     }

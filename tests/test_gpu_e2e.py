@@ -253,6 +253,26 @@ def test_host_entry_point_matches_device_path():
     assert (lab_host == lab_dev.cpu().numpy()).all() and (low_host == low_dev.cpu().numpy()).all()
 
 
+def test_fused_mlp_matches_unfused_path():
+    """ViT-S runs fc1 -> GELU -> fc2 in one fused kernel; the unfused LN / fc1 / fc2 GEMM path (what ViT-B uses)
+    must give the same log-probs up to bf16 rounding noise, and both must match the oracle."""
+    lib = _lib.load()
+    m, cfg, sd = _model("vit_small", 2, 3, "trained_like")
+    x = synthetic.make_frames(2, 240, seed=4).cuda()
+    a = m(x).clone()
+    assert lib.dinoseg_set_fused_mlp(m._handle, 0) == 0
+    b = m(x).clone()
+    assert lib.dinoseg_set_fused_mlp(m._handle, 1) == 0
+    c = m(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a, c)
+    ref = O.forward(sd, cfg, x.cpu())
+    rng = float(ref.max() - ref.min())
+    assert (a - b).abs().max().item() <= 5e-3 * rng
+    assert (a.cpu() - ref).abs().max().item() <= TOL_REL_TRAINED * rng
+    assert (b.cpu() - ref).abs().max().item() <= TOL_REL_TRAINED * rng
+
+
 def test_weight_update_is_picked_up():
     """load_state_dict after the first forward re-packs the bf16 weights (no stale cache)."""
     m, cfg, sd = _model("vit_small", 1, 1, "reference_init")
