@@ -249,6 +249,12 @@ cudaError_t launch_im2col(const float* frames, __nv_bfloat16* A, int B, int g, c
   return cudaGetLastError();
 }
 
+cudaError_t launch_im2col_u8(const uint8_t* frames, __nv_bfloat16* A, int B, int g, const PreprocParams& pp, cudaStream_t s) {
+  const size_t total = size_t(B) * 3 * (g * 8) * g;
+  im2col_u8_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(frames, A, B, g, pp);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_replicate(const uint8_t* lowres, int64_t* labels, int B, int g, int p, cudaStream_t s) {
   const int W = g * p;
   const size_t total = (W & 1) ? size_t(B) * W * W : size_t(B) * W * (W / 2);
@@ -694,8 +700,10 @@ int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind,
 }
 
 // Launch sequence of one forward pass over `batch` frames on the buffers of `w` (already bound).
-static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, int batch, float* logprobs, uint8_t* lowres,
-                        int64_t* labels, cudaStream_t s) {
+// `frames` are normalised fp32 NCHW frames, or (frames == nullptr) `frames_u8` raw uint8 HWC frames that are resized
+// and normalised on the fly (pp).
+static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const uint8_t* frames_u8, const PreprocParams* pp,
+                        int batch, float* logprobs, uint8_t* lowres, int64_t* labels, cudaStream_t s) {
   if (h->res == 0) DSG_FAIL(h, "dinoseg_forward: call dinoseg_set_resolution first");
   if (dinoseg_missing_weights(h) != 0) {
     std::string miss;
@@ -704,7 +712,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, int batc
     DSG_FAIL(h, "dinoseg_forward: %d parameters not set (first missing: %s)", dinoseg_missing_weights(h),
              miss.c_str());
   }
-  if (!frames || batch <= 0) DSG_FAIL(h, "dinoseg_forward: bad arguments");
+  if ((!frames && !(frames_u8 && pp)) || batch <= 0) DSG_FAIL(h, "dinoseg_forward: bad arguments");
   if (size_t(batch) * h->Ntok > size_t(INT32_MAX) / 4) DSG_FAIL(h, "dinoseg_forward: batch too large");
   h->last = &w;
   const int D = h->cfg.embed_dim, HID = h->cfg.mlp_hidden, H = h->cfg.num_heads;
@@ -723,7 +731,12 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, int batc
     p.col_scale = 1.f; p.scale_cols = 0;
     return p;
   };
-  { LaunchScope ls(h, K_IM2COL, s); DSG_CUDA(h, launch_im2col(frames, w.hid, batch, h->g, s)); ++n; }
+  {
+    LaunchScope ls(h, K_IM2COL, s);
+    if (frames) DSG_CUDA(h, launch_im2col(frames, w.hid, batch, h->g, s));
+    else DSG_CUDA(h, launch_im2col_u8(frames_u8, w.hid, batch, h->g, *pp, s));
+    ++n;
+  }
   {
     LaunchScope ls(h, K_CLS, s);
     cls_row_kernel<<<(batch * D + 255) / 256, 256, 0, s>>>(h->cls, h->pos, w.x, batch, h->Ntok, D);
@@ -819,7 +832,8 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
   if (!frames || batch <= 0 || !workspace) DSG_FAIL(h, "dinoseg_forward: bad arguments");
   DSG_CUDA(h, cudaSetDevice(h->device));
   if (bind_workspace(h, h->user, workspace, workspace_bytes, batch) != 0) return -1;
-  return forward_impl(h, h->user, frames, batch, logprobs, lowres, labels, static_cast<cudaStream_t>(stream));
+  return forward_impl(h, h->user, frames, nullptr, nullptr, batch, logprobs, lowres, labels,
+                      static_cast<cudaStream_t>(stream));
 }
 
 // Frames per pipeline chunk: small enough to overlap the copies with the kernels (6..16 frames), and such that
@@ -838,11 +852,13 @@ static int pick_host_chunk(const dinoseg* h, int batch) {
   return best;
 }
 
-int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
-                         int64_t* host_labels, void* stream) {
+// Shared implementation of the host entry points: `host_frames` are fp32 normalised frames (pp == nullptr) or raw
+// uint8 HWC frames of src_h x src_w pixels (pp != nullptr).
+static int predict_host_impl(dinoseg_t* h, const void* host_frames, const PreprocParams* pp, int batch,
+                             uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who) {
   if (!h) return -1;
-  if (h->res == 0) DSG_FAIL(h, "dinoseg_predict_host: call dinoseg_set_resolution first");
-  if (!host_frames || batch <= 0) DSG_FAIL(h, "dinoseg_predict_host: bad arguments");
+  if (h->res == 0) DSG_FAIL(h, "%s: call dinoseg_set_resolution first", who);
+  if (!host_frames || batch <= 0) DSG_FAIL(h, "%s: bad arguments", who);
   DSG_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // The batch is cut into chunks that go round-robin through three lanes (stream + staging + workspace
@@ -850,7 +866,7 @@ int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint
   // of one lane overlap the kernels of the other.  Frames are independent, so chunking does not change
   // any result bit.
   const int chunk = pick_host_chunk(h, batch);
-  const size_t frame_elems = size_t(3) * h->res * h->res;
+  const size_t frame_bytes = pp ? size_t(pp->src_h) * pp->src_w * 3 : size_t(3) * h->res * h->res * sizeof(float);
   const size_t W = size_t(h->g) * h->p_rep;
   const size_t label_elems = W * W;
   const size_t wbytes = dinoseg_workspace_bytes(h, chunk);
@@ -869,7 +885,7 @@ int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint
     if (!l.stream) DSG_CUDA(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     if (!l.done) DSG_CUDA(h, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     const size_t ws_before = l.ws_cap;
-    DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.frames), &l.frames_cap, size_t(chunk) * frame_elems * sizeof(float)));
+    DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.frames), &l.frames_cap, size_t(chunk) * frame_bytes));
     DSG_CUDA(h, grow(l, &l.ws, &l.ws_cap, wbytes));
     DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.lowres), &l.lowres_cap, size_t(chunk) * h->P));
     if (host_labels && label_elems)
@@ -883,11 +899,11 @@ int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint
     HostLane& l = h->lanes[c % nlanes];
     const int f0 = c * chunk;
     const int nb = (batch - f0) < chunk ? (batch - f0) : chunk;
-    DSG_CUDA(h, cudaMemcpyAsync(l.frames, host_frames + size_t(f0) * frame_elems, size_t(nb) * frame_elems * sizeof(float),
-                                cudaMemcpyHostToDevice, l.stream));
+    DSG_CUDA(h, cudaMemcpyAsync(l.frames, static_cast<const uint8_t*>(host_frames) + size_t(f0) * frame_bytes,
+                                size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, l.stream));
     if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
-    if (forward_impl(h, l.bufs, l.frames, nb, nullptr, l.lowres, (host_labels && label_elems) ? l.labels : nullptr,
-                     l.stream) != 0)
+    if (forward_impl(h, l.bufs, pp ? nullptr : l.frames, pp ? reinterpret_cast<const uint8_t*>(l.frames) : nullptr, pp, nb,
+                     nullptr, l.lowres, (host_labels && label_elems) ? l.labels : nullptr, l.stream) != 0)
       return -1;
     if (host_lowres)
       DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
@@ -902,6 +918,43 @@ int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint
   }
   for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamSynchronize(h->lanes[k].stream));
   return 0;
+}
+
+static int make_preproc(dinoseg_t* h, int src_h, int src_w, const float* mean, const float* std_, PreprocParams* pp) {
+  if (src_h < 1 || src_w < 1 || src_h > 16384 || src_w > 16384 || !mean || !std_) DSG_FAIL(h, "bad preprocessing arguments");
+  pp->src_h = src_h; pp->src_w = src_w;
+  for (int c = 0; c < 3; ++c) {
+    // albumentations Normalize: mean * 255 and 1 / (std * 255), both in float32
+    pp->mean255[c] = mean[c] * 255.0f;
+    pp->denom[c] = 1.0f / (std_[c] * 255.0f);
+  }
+  return 0;
+}
+
+int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
+                         int64_t* host_labels, void* stream) {
+  return predict_host_impl(h, host_frames, nullptr, batch, host_lowres, host_labels, stream, "dinoseg_predict_host");
+}
+
+int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames, int batch, int src_h, int src_w, const float* mean,
+                            const float* std_, uint8_t* host_lowres, int64_t* host_labels, void* stream) {
+  if (!h) return -1;
+  PreprocParams pp;
+  if (make_preproc(h, src_h, src_w, mean, std_, &pp) != 0) return -1;
+  return predict_host_impl(h, host_frames, &pp, batch, host_lowres, host_labels, stream, "dinoseg_predict_host_u8");
+}
+
+int dinoseg_forward_u8(dinoseg_t* h, const uint8_t* frames, int batch, int src_h, int src_w, const float* mean,
+                       const float* std_, float* logprobs, uint8_t* lowres, int64_t* labels, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!h) return -1;
+  if (h->res == 0) DSG_FAIL(h, "dinoseg_forward_u8: call dinoseg_set_resolution first");
+  if (!frames || batch <= 0 || !workspace) DSG_FAIL(h, "dinoseg_forward_u8: bad arguments");
+  PreprocParams pp;
+  if (make_preproc(h, src_h, src_w, mean, std_, &pp) != 0) return -1;
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  if (bind_workspace(h, h->user, workspace, workspace_bytes, batch) != 0) return -1;
+  return forward_impl(h, h->user, nullptr, frames, &pp, batch, logprobs, lowres, labels, static_cast<cudaStream_t>(stream));
 }
 
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk) {

@@ -133,6 +133,81 @@ __global__ void im2col_patch8_kernel(const float* __restrict__ frames, __nv_bflo
   *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K + 8) = h1;
 }
 
+// ---------------------------------------------------------------------------------------
+// Preprocessing of DINOSeg.predict fused into the im2col (reference pl_torch_modules.py:33-41, :291):
+//   uint8 HWC RGB frame [H, W, 3] -> albumentations Resize(r, r) = cv2.resize(INTER_LINEAR) ->
+//   Normalize: (pix - mean*255) * (1 / (std*255)) in fp32 -> CHW -> 8x8 patches (bf16x3 operand as above).
+// The resize reproduces OpenCV's 8-bit bilinear path in integer arithmetic: source coordinate
+// (d + 0.5) * src/dst - 0.5, taps clamped at the borders, 11-bit fixed-point weights
+// (INTER_RESIZE_COEF_BITS), horizontal pass in int32, vertical pass
+// ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2, i.e. the uint8 image cv2 would hand to
+// Normalize.  Same-size frames (H = W = r) pass through exactly.  One thread = 8 output pixels of one row.
+// ---------------------------------------------------------------------------------------
+struct PreprocParams {
+  int src_h, src_w;
+  float mean255[3];     // float32(mean) * 255
+  float denom[3];       // 1 / (float32(std) * 255)
+};
+
+// cv::resize INTER_LINEAR coefficients for destination index d: f = (d + 0.5) * scale - 0.5 (in fp32), s = floor(f),
+// weights saturate_cast<short>(w * 2048) (round half to even).  Horizontally OpenCV zeroes the fraction at the
+// borders, vertically it only clamps the two rows.
+__device__ __forceinline__ void cv_linear_coef(int d, double scale, int src_size, bool horizontal, int& s0, int& s1,
+                                               int& a0, int& a1) {
+  float f = float((double(d) + 0.5) * scale - 0.5);
+  int sx = int(floorf(f));
+  f -= float(sx);
+  if (horizontal) {
+    if (sx < 0) { f = 0.f; sx = 0; }
+    if (sx >= src_size - 1) { f = 0.f; sx = src_size - 1; }
+  }
+  s0 = min(max(sx, 0), src_size - 1);
+  s1 = min(max(sx + 1, 0), src_size - 1);
+  a0 = __float2int_rn((1.f - f) * 2048.f);
+  a1 = __float2int_rn(f * 2048.f);
+}
+
+__global__ void im2col_u8_kernel(const uint8_t* __restrict__ frames /*[B, H, W, 3]*/, __nv_bfloat16* __restrict__ A,
+                                 int B, int g, PreprocParams pp) {
+  const int r = g * 8;
+  const size_t total = size_t(B) * 3 * r * g;      // (b, c, y, j): 8 pixels each
+  size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = int(idx % g); idx /= g;
+  const int y = int(idx % r); idx /= r;
+  const int c = int(idx % 3);
+  const int b = int(idx / 3);
+  const uint8_t* src = frames + size_t(b) * pp.src_h * pp.src_w * 3;
+  const bool same = pp.src_h == r && pp.src_w == r;
+  const double sy = double(pp.src_h) / double(r), sx = double(pp.src_w) / double(r);
+  int y0, y1, b0, b1;
+  cv_linear_coef(y, sy, pp.src_h, false, y0, y1, b0, b1);
+  float v[8];
+#pragma unroll
+  for (int kx = 0; kx < 8; ++kx) {
+    const int x = j * 8 + kx;
+    int pix;
+    if (same) {
+      pix = src[(size_t(y) * pp.src_w + x) * 3 + c];
+    } else {
+      int x0, x1, a0, a1;
+      cv_linear_coef(x, sx, pp.src_w, true, x0, x1, a0, a1);
+      const int r0 = int(src[(size_t(y0) * pp.src_w + x0) * 3 + c]) * a0 + int(src[(size_t(y0) * pp.src_w + x1) * 3 + c]) * a1;
+      const int r1 = int(src[(size_t(y1) * pp.src_w + x0) * 3 + c]) * a0 + int(src[(size_t(y1) * pp.src_w + x1) * 3 + c]) * a1;
+      pix = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+      pix = pix < 0 ? 0 : (pix > 255 ? 255 : pix);
+    }
+    v[kx] = (float(pix) - pp.mean255[c]) * pp.denom[c];
+  }
+  uint4 hi, lo;
+  split_pack8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+  const int i = y >> 3, ky = y & 7;
+  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * IM2COL_K3 + c * 64 + ky * 8;
+  *reinterpret_cast<uint4*>(dst) = hi;
+  *reinterpret_cast<uint4*>(dst + IM2COL_K) = lo;
+  *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K) = hi;
+}
+
 // x[b*Ntok + 0, :] = cls + pos[0]      (reference vision_transformer.py:229-233)
 __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                                int B, int Ntok, int D) {

@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib
 from .synthetic import ARCHS
-from .transforms import get_transforms
+from .transforms import IMAGENET_MEAN, IMAGENET_STD, get_transforms
 
 
 # ------------------------------------------------------------------------------------------
@@ -337,11 +337,77 @@ class DINOSeg(nn.Module):
         """Run inference on a single image (pl_torch_modules.py:276-300).
 
         x : PIL.Image (or HxWx3 uint8 array).  Returns an int64 ndarray of shape
-        [g*p, g*p] (480x480 for resolutions 240/480/960)."""
-        img = self.transforms(image=np.array(x))['image']
-        frames = img.unsqueeze(0).to(self.device)
-        _, _, lab = self.infer(frames, want_logprobs=False, want_labels=True)
+        [g*p, g*p] (480x480 for resolutions 240/480/960).
+
+        The reference's transforms (Resize -> Normalize -> ToTensorV2, :33-41) run on the GPU, fused into the
+        patch-embed im2col (bit-exact w.r.t. cv2.resize(INTER_LINEAR) + the fp32 normalisation); `self.transforms`
+        stays available for callers that use it directly (visualize_attention.py:45)."""
+        img = np.asarray(x)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+            # not a plain RGB uint8 image: host transforms + fp32 path, as the reference does
+            t = self.transforms(image=img)['image']
+            _, _, lab = self.infer(t.unsqueeze(0).to(self.device), want_logprobs=False, want_labels=True)
+            return lab[0].cpu().numpy()
+        frames = torch.from_numpy(np.array(img, copy=True)).unsqueeze(0).to(self.device)
+        _, _, lab = self.infer_u8(frames, self.resolution, want_logprobs=False, want_labels=True)
         return lab[0].cpu().numpy()
+
+    @torch.no_grad()
+    def infer_u8(self, frames_u8, resolution=None, want_logprobs=True, want_lowres=False, want_labels=False):
+        """Hot path on RAW device frames: uint8 [B,H,W,3] RGB (any H, W) -> resize to `resolution`, normalise
+        (ImageNet), forward.  Returns (logprobs, lowres, labels) like infer()."""
+        lib = self._ensure_handle()
+        if frames_u8.dim() != 4 or frames_u8.shape[3] != 3 or frames_u8.dtype != torch.uint8:
+            raise ValueError(f"expected uint8 frames of shape [B,H,W,3], got {tuple(frames_u8.shape)} {frames_u8.dtype}")
+        if frames_u8.device != self.device:
+            raise ValueError(f"frames are on {frames_u8.device}, model on {self.device}")
+        res = int(self.resolution if resolution is None else resolution)
+        frames_u8 = frames_u8.contiguous()
+        b, sh, sw = int(frames_u8.shape[0]), int(frames_u8.shape[1]), int(frames_u8.shape[2])
+        self._ensure_resolution(lib, res)
+        ws = self._ensure_workspace(lib, b)
+        g = res // 8
+        p = 480 // g
+        dev = self.device
+        lp = torch.empty((b * g * g, self.n_classes), dtype=torch.float32, device=dev) if want_logprobs else None
+        low = torch.empty((b, g, g), dtype=torch.uint8, device=dev) if want_lowres else None
+        lab = torch.empty((b, g * p, g * p), dtype=torch.int64, device=dev) if want_labels else None
+        mean = (C.c_float * 3)(*IMAGENET_MEAN)
+        std = (C.c_float * 3)(*IMAGENET_STD)
+        rc = lib.dinoseg_forward_u8(self._handle, frames_u8.data_ptr(), b, sh, sw, mean, std,
+                                    lp.data_ptr() if lp is not None else None,
+                                    low.data_ptr() if low is not None else None,
+                                    lab.data_ptr() if lab is not None else None,
+                                    ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, "dinoseg_forward_u8")
+        return lp, low, lab
+
+    def predict_batch_u8(self, frames_u8, resolution=None, output="labels", out=None):
+        """Batched predict() on raw HOST frames: uint8 [B,H,W,3] (ideally pinned) -> numpy label maps; resize,
+        normalisation, forward, argmax and replication on the GPU, copies pipelined with the kernels."""
+        if output not in ("labels", "lowres"):
+            raise ValueError(output)
+        lib = self._ensure_handle()
+        if frames_u8.dim() != 4 or frames_u8.shape[3] != 3 or frames_u8.dtype != torch.uint8 or frames_u8.device.type != "cpu":
+            raise ValueError("expected CPU uint8 frames of shape [B,H,W,3]")
+        frames_u8 = frames_u8.contiguous()
+        res = int(self.resolution if resolution is None else resolution)
+        b, sh, sw = int(frames_u8.shape[0]), int(frames_u8.shape[1]), int(frames_u8.shape[2])
+        self._ensure_resolution(lib, res)
+        g = res // 8
+        p = 480 // g
+        shape, dtype = ((b, g * p, g * p), torch.int64) if output == "labels" else ((b, g, g), torch.uint8)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+        elif tuple(out.shape) != shape or out.dtype != dtype or out.device.type != "cpu" or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous CPU tensor of shape {shape} and dtype {dtype}")
+        mean = (C.c_float * 3)(*IMAGENET_MEAN)
+        std = (C.c_float * 3)(*IMAGENET_STD)
+        rc = lib.dinoseg_predict_host_u8(self._handle, frames_u8.data_ptr(), b, sh, sw, mean, std,
+                                         out.data_ptr() if output == "lowres" else None,
+                                         out.data_ptr() if output == "labels" else None, self._stream())
+        self._check(rc, "dinoseg_predict_host_u8")
+        return out.numpy()
 
     def predict_batch(self, frames, output="labels", out=None):
         """Batched counterpart of predict() for already-normalised frames [B,3,r,r].

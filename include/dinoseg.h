@@ -81,6 +81,18 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
 int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
                          int64_t* host_labels, void* stream);
 
+/* The same two calls on RAW camera frames: uint8 RGB, HWC, [batch, src_h, src_w, 3].  Replaces the inference
+ * transforms of DINOSeg.predict (pl_torch_modules.py:33-41, :291: albumentations Resize(r, r) -> Normalize(mean, std)
+ * -> ToTensorV2) on the GPU, fused into the patch-embed im2col: the bilinear resize reproduces cv2.resize(INTER_LINEAR)
+ * on 8-bit images bit for bit (11-bit fixed-point weights, result rounded to uint8), the normalisation is
+ * (pix - mean*255) * (1 / (std*255)) in fp32.  mean / std: 3 host floats each (ImageNet values in the reference). */
+int dinoseg_forward_u8(dinoseg_t* h, const uint8_t* frames_u8, int batch, int src_h, int src_w, const float* mean,
+                       const float* std_, float* logprobs, uint8_t* lowres, int64_t* labels, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames_u8, int batch, int src_h, int src_w,
+                            const float* mean, const float* std_, uint8_t* host_lowres, int64_t* host_labels,
+                            void* stream);
+
 /* Frames per pipeline chunk of dinoseg_predict_host (0 = automatic, the default): the host batch is processed in chunks
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);

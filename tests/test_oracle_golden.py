@@ -97,3 +97,20 @@ def test_flops_formula_matches_baseline_md():
     assert abs(O.flops_per_frame(cfg1, 240) / 1e9 - 4.744) < 0.01
     cfgb = synthetic.make_config("vit_base", 4, 7)
     assert abs(O.flops_per_frame(cfgb, 480) / 1e9 - 365.56) < 0.05
+
+
+@pytest.mark.parametrize("hw,res", [((480, 640), 480), ((480, 640), 240), ((480, 640), 960), ((600, 800), 480),
+                                    ((123, 77), 64), ((480, 480), 240), ((1080, 1920), 480), ((480, 640), 496),
+                                    ((480, 480), 480)])
+def test_preprocessing_oracle_matches_cv2_and_transforms(hw, res):
+    """The integer restatement of OpenCV's 8-bit bilinear resize is bit-exact w.r.t. cv2.resize(INTER_LINEAR)
+    (what albumentations.Resize calls), and the full preprocessing equals dino_b200.transforms (the host path)."""
+    import cv2
+    from oracle import preproc_oracle as P
+    from dino_b200.transforms import get_transforms
+    rng = np.random.default_rng(hw[0] * 7 + res)
+    img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    ref = cv2.resize(img, dsize=(res, res), interpolation=cv2.INTER_LINEAR)
+    assert (P.resize_linear_u8(img, res) == ref).all()
+    t = get_transforms(res)(image=img)["image"].numpy()
+    assert np.array_equal(P.preprocess(img, res), t)
