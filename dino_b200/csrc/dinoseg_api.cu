@@ -140,6 +140,7 @@ cudaError_t launch_mlp_fused(const CUtensorMap& a, const CUtensorMap& w1, const 
   return cudaGetLastError();
 }
 
+constexpr int kLinPitch = 16;    // row pitch (floats) of the 'linear' head's logits buffer (n_classes <= 16)
 constexpr int kHeadPart = 256;   // width of each bf16x3 part of relu(layer_1) (head_h1 <= 256, zero padded)
 
 template <int EPI, bool RES_A>
@@ -193,6 +194,7 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, con
     case EPI_PATCH_F32: return launch_gemm_t<EPI_PATCH_F32>(a, w, out, add, p, num_sms, s);
     case EPI_RELU_F32: return launch_gemm_t<EPI_RELU_F32>(a, w, out, add, p, num_sms, s);
     case EPI_RELU_SPLIT_BF16: return launch_gemm_t<EPI_RELU_SPLIT_BF16>(a, w, out, add, p, num_sms, s);
+    case EPI_BIAS_F32: return launch_gemm_t<EPI_BIAS_F32>(a, w, out, add, p, num_sms, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -292,7 +294,7 @@ struct WorkBufs {
   uint8_t* lowres = nullptr;        // [B*P]
   CUtensorMap tm_im2col, tm_abuf, tm_hid, tm_qkv3d;                                  // A operands / attention
   CUtensorMap tm_x_out, tm_x_patch, tm_pos_add, tm_qkv_out, tm_hid_out;              // GEMM outputs / addends
-  CUtensorMap tm_qkv_a, tm_h1s_out, tm_h1s_a, tm_h2_out;                             // segmentation head
+  CUtensorMap tm_qkv_a, tm_h1s_out, tm_h1s_a, tm_h2_out, tm_lin_out;                 // segmentation head
 };
 
 // predict_host pipeline lane: own stream, device staging and workspace, so that the copies of one
@@ -426,6 +428,7 @@ int bind_workspace(dinoseg* h, WorkBufs& w, void* ws, size_t ws_bytes, int batch
   ok &= make_tmap_gemm_out(&w.tm_h1s_out, w.hid, false, 3 * kHeadPart, M, 1, 3 * kHeadPart);
   ok &= make_tmap_gemm_a(&w.tm_h1s_a, w.hid, M, 1, 3 * kHeadPart);
   ok &= make_tmap_gemm_out(&w.tm_h2_out, w.x, true, h->cfg.head_h2, M, 1, h->cfg.head_h2);
+  ok &= make_tmap_gemm_out(&w.tm_lin_out, w.x, true, h->cfg.n_classes, M, 1, kLinPitch);   // 'linear' head logits
   (void)H1;
   if (!ok) DSG_FAIL(h, "cuTensorMapEncodeTiled failed for the workspace tensor maps");
   w.base = ws;
@@ -485,7 +488,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   if (cfg->patch != 8) DSG_FAIL(null_h, "patch size must be 8");
   if (cfg->n_blocks < 0 || cfg->n_blocks > 12) DSG_FAIL(null_h, "n_blocks out of range");
   if (cfg->n_classes < 1 || cfg->n_classes > HEAD_MAX_C) DSG_FAIL(null_h, "n_classes must be in [1,%d]", HEAD_MAX_C);
-  if (cfg->head_kind != 0) DSG_FAIL(null_h, "only the 'mlp' head (head_kind=0) is implemented");
+  if (cfg->head_kind != 0 && cfg->head_kind != 1) DSG_FAIL(null_h, "head_kind must be 0 ('mlp') or 1 ('linear')");
   if (cfg->head_h1 % 8 != 0 || cfg->head_h1 < 8 || cfg->head_h1 > kHeadPart || cfg->head_h2 % 4 != 0 ||
       cfg->head_h2 > HT_MAX_H2 || cfg->head_h2 < 4)
     DSG_FAIL(null_h, "unsupported head widths %d/%d", cfg->head_h1, cfg->head_h2);
@@ -499,7 +502,8 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
   h->num_sms = prop.multiProcessorCount;
   const int D = cfg->embed_dim, HID = cfg->mlp_hidden, G0 = cfg->pos_grid, C = cfg->n_classes;
-  const int H1 = cfg->head_h1, H2 = cfg->head_h2;
+  const bool linear_head = cfg->head_kind == 1;          // reference pl_torch_modules.py:127-138: Linear(D, C)
+  const int H1 = linear_head ? C : cfg->head_h1, H2 = cfg->head_h2;
   int rc = 0;
   rc |= dev_alloc(h, &h->cls, D);
   rc |= dev_alloc(h, &h->pos_src, size_t(G0 * G0 + 1) * D);
@@ -521,10 +525,12 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   add_slot(h, "dino.norm.bias", 0, h->norm_b, {D});
   add_slot(h, "clf.layer_1.weight", 3, h->h1_w, {H1, D});
   add_slot(h, "clf.layer_1.bias", 0, h->h1_b, {H1});
-  add_slot(h, "clf.layer_2.weight", 4, h->h2_w, {H2, H1});
-  add_slot(h, "clf.layer_2.bias", 0, h->b2, {H2});
-  add_slot(h, "clf.layer_3.weight", 0, h->w3, {C, H2});
-  add_slot(h, "clf.layer_3.bias", 0, h->b3, {C});
+  if (!linear_head) {
+    add_slot(h, "clf.layer_2.weight", 4, h->h2_w, {H2, H1});
+    add_slot(h, "clf.layer_2.bias", 0, h->b2, {H2});
+    add_slot(h, "clf.layer_3.weight", 0, h->w3, {C, H2});
+    add_slot(h, "clf.layer_3.bias", 0, h->b3, {C});
+  }
   h->blocks.resize(cfg->n_blocks);
   for (int i = 0; i < cfg->n_blocks && rc == 0; ++i) {
     BlockW& b = h->blocks[i];
@@ -800,19 +806,31 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
   // The head runs in "bf16x3" precision (operands split into hi + lo bf16 parts, three-fold K): its plain
   // bf16 rounding would otherwise be the largest contribution to the log-prob error.
   { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, h->norm_g, h->norm_b, w.qkv, M, D, eps, true, s)); ++n; }
-  {
-    GemmParams p = gp(h->cfg.head_h1, 3 * D, h->h1_b);
-    p.split_part = kHeadPart;
-    LaunchScope ls(h, K_GEMM_HEAD, s);
-    DSG_CUDA(h, launch_gemm(EPI_RELU_SPLIT_BF16, w.tm_qkv_a, h->tm_h1, w.tm_h1s_out, w.tm_h1s_out, p, sms, s)); ++n;
-  }
-  {
-    GemmParams p = gp(h->cfg.head_h2, 3 * kHeadPart, h->b2);
-    LaunchScope ls(h, K_GEMM_HEAD, s);
-    DSG_CUDA(h, launch_gemm(EPI_RELU_F32, w.tm_h1s_a, h->tm_h2, w.tm_h2_out, w.tm_h2_out, p, sms, s)); ++n;
-  }
   uint8_t* lr = lowres ? lowres : w.lowres;
-  {
+  if (h->cfg.head_kind == 1) {
+    // 'linear' head (pl_torch_modules.py:127-138): one bf16x3 GEMM -> logits [M, C] (row pitch kLinPitch) -> log_softmax
+    {
+      GemmParams p = gp(h->cfg.n_classes, 3 * D, h->h1_b);
+      LaunchScope ls(h, K_GEMM_HEAD, s);
+      DSG_CUDA(h, launch_gemm(EPI_BIAS_F32, w.tm_qkv_a, h->tm_h1, w.tm_lin_out, w.tm_lin_out, p, sms, s)); ++n;
+    }
+    const int rows = batch * h->P;
+    LaunchScope ls(h, K_HEAD_TAIL, s);
+    linear_tail_kernel<<<(rows + 255) / 256, 256, 0, s>>>(w.x, kLinPitch, logprobs, lr, batch, h->P, h->Ntok,
+                                                          h->cfg.n_classes);
+    DSG_CUDA(h, cudaGetLastError()); ++n;
+  } else {
+    {
+      GemmParams p = gp(h->cfg.head_h1, 3 * D, h->h1_b);
+      p.split_part = kHeadPart;
+      LaunchScope ls(h, K_GEMM_HEAD, s);
+      DSG_CUDA(h, launch_gemm(EPI_RELU_SPLIT_BF16, w.tm_qkv_a, h->tm_h1, w.tm_h1s_out, w.tm_h1s_out, p, sms, s)); ++n;
+    }
+    {
+      GemmParams p = gp(h->cfg.head_h2, 3 * kHeadPart, h->b2);
+      LaunchScope ls(h, K_GEMM_HEAD, s);
+      DSG_CUDA(h, launch_gemm(EPI_RELU_F32, w.tm_h1s_a, h->tm_h2, w.tm_h2_out, w.tm_h2_out, p, sms, s)); ++n;
+    }
     const int rows = batch * h->P;
     const int grid = (rows + 255) / 256;
     LaunchScope ls(h, K_HEAD_TAIL, s);

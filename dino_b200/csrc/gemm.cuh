@@ -35,6 +35,7 @@ enum : int {
   EPI_PATCH_F32 = 3,  // out f32[b, 1 + t] = acc + bias + pos[1 + t]   (addend = positional table)
   EPI_RELU_F32 = 4,   // out f32 = relu(acc + bias)
   EPI_RELU_SPLIT_BF16 = 5,  // v = relu(acc + bias); out bf16 [rows, 3*split_part] = [hi(v) | lo(v) | hi(v)] (bf16x3 operand)
+  EPI_BIAS_F32 = 6,   // out f32 = acc + bias
 };
 
 struct GemmParams {
@@ -72,7 +73,7 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 128 * 128;             // one staging buffer: 128 rows x 128 bytes
 
 __host__ __device__ constexpr bool gemm_out_is_f32(int epi) {
-  return epi == EPI_RESID_F32 || epi == EPI_PATCH_F32 || epi == EPI_RELU_F32;
+  return epi == EPI_RESID_F32 || epi == EPI_PATCH_F32 || epi == EPI_RELU_F32 || epi == EPI_BIAS_F32;
 }
 __host__ __device__ constexpr bool gemm_has_addend(int epi) { return epi == EPI_RESID_F32 || epi == EPI_PATCH_F32; }
 __host__ __device__ constexpr int gemm_nbuf(int epi) {

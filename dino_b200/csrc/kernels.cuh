@@ -347,6 +347,37 @@ head_tail_kernel(const float* __restrict__ h2 /*[B*Ntok, H2]*/, const float* __r
   }
 }
 
+// 'linear' head tail (reference pl_torch_modules.py:135-138): logits z [B*Ntok, ldz] (cls rows included, C valid
+// columns) -> log_softmax -> argmax.  One thread per patch row.
+__global__ void __launch_bounds__(256)
+linear_tail_kernel(const float* __restrict__ z, int ldz, float* __restrict__ logprobs, uint8_t* __restrict__ lowres,
+                   int B, int P, int Ntok, int C) {
+  const int total_rows = B * P;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_rows; r += gridDim.x * blockDim.x) {
+    const int b = r / P, t = r - b * P;
+    const float* src = z + (size_t(b) * Ntok + 1 + t) * ldz;
+    float v[HEAD_MAX_C];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_C; ++c)
+      if (c < C) { v[c] = src[c]; mx = fmaxf(mx, v[c]); }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_C; ++c)
+      if (c < C) se += expf(v[c] - mx);
+    const float lse = logf(se);
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_C; ++c)
+      if (c < C) v[c] = (v[c] - mx) - lse;
+    if (logprobs != nullptr) {
+#pragma unroll
+      for (int c = 0; c < HEAD_MAX_C; ++c)
+        if (c < C) logprobs[size_t(r) * C + c] = v[c];
+    }
+    if (lowres != nullptr) lowres[r] = uint8_t(argmax_first(v, C));
+  }
+}
+
 // log-probs [rows, C] -> label per row (torch.argmax semantics)
 __global__ void argmax_rows_kernel(const float* __restrict__ logprobs, uint8_t* __restrict__ lowres, int rows,
                                    int C) {

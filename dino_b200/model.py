@@ -97,6 +97,14 @@ class _MLPHead(nn.Module):
         self.layer_3 = nn.Linear(100, n_classes)
 
 
+class _LinearHead(nn.Module):
+    """pl_torch_modules.py:127-138."""
+
+    def __init__(self, n_classes, input_dim):
+        super().__init__()
+        self.layer_1 = nn.Linear(input_dim, n_classes)
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     """PL checkpoints pickle ctor kwargs (optimizer class, loggers...).  Classes from packages
     that are not installed are replaced by inert placeholders instead of failing the load."""
@@ -130,9 +138,8 @@ class DINOSeg(nn.Module):
         super().__init__()
         if backbone != 'vit':
             raise NotImplementedError("only backbone='vit' is part of the B200 hot path (cnn1/cnn2 are ablations)")
-        if head != 'mlp':
-            raise NotImplementedError("only head='mlp' is implemented on the B200 path "
-                                      "(every shipped configuration of the reference uses it)")
+        if head not in ('mlp', 'linear'):
+            raise ValueError(f"unknown head {head!r} (reference: 'linear' or 'mlp', pl_torch_modules.py:219-222)")
         if arch not in ARCHS:
             raise ValueError(f"unknown arch {arch!r}")
         self.n_blocks = n_blocks
@@ -166,7 +173,7 @@ class DINOSeg(nn.Module):
         # network: parameters start from the reference's random init and are expected to be
         # overwritten by load_from_checkpoint / load_state_dict.
         self.dino = _Backbone(a["embed_dim"], a["mlp_hidden"], a["num_heads"], n_blocks)
-        self.clf = _MLPHead(n_classes, a["embed_dim"])
+        self.clf = _MLPHead(n_classes, a["embed_dim"]) if head == 'mlp' else _LinearHead(n_classes, a["embed_dim"])
         for p in self.parameters():
             p.requires_grad_(False)
 
@@ -218,8 +225,8 @@ class DINOSeg(nn.Module):
     def _cfg(self):
         a = ARCHS[self.arch]
         return _lib.DinosegCfg(a["embed_dim"], a["num_heads"], a["mlp_hidden"], self.n_blocks, 8,
-                               int(round((self.dino.pos_embed.shape[1] - 1) ** 0.5)), self.n_classes, 200, 100, 0,
-                               1e-6)
+                               int(round((self.dino.pos_embed.shape[1] - 1) ** 0.5)), self.n_classes, 200, 100,
+                               0 if self.head == 'mlp' else 1, 1e-6)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -28,10 +28,10 @@ ARCHS = {
 }
 
 
-def make_config(arch: str = "vit_small", n_blocks: int = 3, n_classes: int = 7) -> dict:
+def make_config(arch: str = "vit_small", n_blocks: int = 3, n_classes: int = 7, head: str = "mlp") -> dict:
     cfg = dict(ARCHS[arch])
     cfg.update(arch=arch, n_blocks=n_blocks, n_classes=n_classes, patch=8, pos_grid=28,
-               head_h1=200, head_h2=100, head="mlp", ln_eps=1e-6)
+               head_h1=200, head_h2=100, head=head, ln_eps=1e-6)
     return cfg
 
 
@@ -82,7 +82,9 @@ def init_state_dict(cfg: dict, seed: int = 0, variant: str = "reference_init") -
         lin(p + "mlp.fc1", HID, D, 0.02 if not tl else 0.05)
         lin(p + "mlp.fc2", D, HID, 0.02 if not tl else 0.03)
     ln("dino.norm")
-    for name, (o, i_) in (("clf.layer_1", (H1, D)), ("clf.layer_2", (H2, H1)), ("clf.layer_3", (C, H2))):
+    layers = (("clf.layer_1", (H1, D)), ("clf.layer_2", (H2, H1)), ("clf.layer_3", (C, H2))) if cfg.get("head", "mlp") == "mlp" \
+        else (("clf.layer_1", (C, D)),)      # 'linear' head: pl_torch_modules.py:127-138
+    for name, (o, i_) in layers:
         b = 1.0 / math.sqrt(i_)
         sd[name + ".weight"] = _uni(g, (o, i_), b)
         sd[name + ".bias"] = _uni(g, (o,), b)

@@ -158,7 +158,9 @@ def backbone(sd: dict, cfg: dict, x: torch.Tensor, stages: dict | None = None) -
 
 
 def head(sd: dict, x: torch.Tensor) -> torch.Tensor:
-    """MLP head, pl_torch_modules.py:117-124."""
+    """MLP head, pl_torch_modules.py:117-124; 'linear' head (no layer_2 in the state_dict), :135-138."""
+    if "clf.layer_2.weight" not in sd:
+        return F.log_softmax(F.linear(x, sd["clf.layer_1.weight"], sd["clf.layer_1.bias"]), dim=1)
     x = F.relu(F.linear(x, sd["clf.layer_1.weight"], sd["clf.layer_1.bias"]))
     x = F.relu(F.linear(x, sd["clf.layer_2.weight"], sd["clf.layer_2.bias"]))
     x = F.linear(x, sd["clf.layer_3.weight"], sd["clf.layer_3.bias"])

@@ -39,6 +39,7 @@ CASES = [
     ("s8_nb3_480_refinit", "vit_small", 3, 480, 1, "reference_init", 5),
     ("b8_nb4_240_trained", "vit_base", 4, 240, 1, "trained_like", 6),
     ("b8_nb4_240_refinit", "vit_base", 4, 240, 1, "reference_init", 8),
+    ("s8_nb1_240_linear5_refinit", "vit_small", 1, 240, 2, "reference_init", 9),      # head='linear', 5 classes
 ]
 
 
@@ -52,7 +53,7 @@ def sample_rows(n_tok: int, k: int = 24) -> np.ndarray:
 def build_reference_model(plm, vt, cfg, sd):
     """The reference's own modules, loaded with our synthetic state_dict."""
     if cfg["arch"] == "vit_small":
-        m = plm.DINOSeg(data_path="d", write_path="w", head="mlp", n_blocks=cfg["n_blocks"],
+        m = plm.DINOSeg(data_path="d", write_path="w", head=cfg["head"], n_blocks=cfg["n_blocks"],
                         n_classes=cfg["n_classes"], random_init=True)
     else:
         # the reference hard-codes ViT-S in DINOSeg; ViT-B is composed from its own parts
@@ -71,7 +72,9 @@ def build_reference_model(plm, vt, cfg, sd):
 
 
 def run_case(plm, vt, name, arch, n_blocks, res, batch, variant, seed):
-    cfg = synthetic.make_config(arch, n_blocks, 7)
+    linear = "linear" in name
+    n_classes = 5 if linear else 7
+    cfg = synthetic.make_config(arch, n_blocks, n_classes, head="linear" if linear else "mlp")
     sd = synthetic.init_state_dict(cfg, seed, variant)
     x = synthetic.make_frames(batch, res, seed)
     m = build_reference_model(plm, vt, cfg, sd)
@@ -88,7 +91,7 @@ def run_case(plm, vt, name, arch, n_blocks, res, batch, variant, seed):
     high = np.stack([np.kron(low[b], np.ones((p, p), dtype=int)) for b in range(batch)])
     rows = sample_rows(g * g + 1)
     meta = dict(name=name, arch=arch, n_blocks=n_blocks, res=res, batch=batch, variant=variant, seed=seed,
-                n_classes=7, torch=torch.__version__)
+                n_classes=n_classes, head=cfg["head"], torch=torch.__version__)
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
         meta=json.dumps(meta),
@@ -103,7 +106,7 @@ def run_case(plm, vt, name, arch, n_blocks, res, batch, variant, seed):
         blk0_rows=blk0[:, rows].numpy().astype(np.float32),
         norm_rows=normed[:, rows].numpy().astype(np.float32),
     )
-    hist = np.bincount(low.reshape(-1), minlength=7).tolist()
+    hist = np.bincount(low.reshape(-1), minlength=n_classes).tolist()
     print(f"{name}: logprobs {tuple(lp.shape)} range [{lp.min():.3f},{lp.max():.3f}] label hist {hist}")
 
 

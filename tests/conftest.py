@@ -31,4 +31,5 @@ def load_golden(name):
 GOLDEN_CASES = [
     "s8_nb1_240_refinit", "s8_nb3_480_trained", "s8_nb3_240_b2_trained", "s8_nb2_224_trained",
     "s8_nb1_64_trained", "s8_nb3_480_refinit", "b8_nb4_240_trained", "b8_nb4_240_refinit",
+    "s8_nb1_240_linear5_refinit",
 ]

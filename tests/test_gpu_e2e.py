@@ -52,10 +52,10 @@ def _record(**kw):
         pass
 
 
-def _model(arch, n_blocks, seed, variant, n_classes=7):
-    cfg = synthetic.make_config(arch, n_blocks, n_classes)
+def _model(arch, n_blocks, seed, variant, n_classes=7, head="mlp"):
+    cfg = synthetic.make_config(arch, n_blocks, n_classes, head=head)
     sd = synthetic.init_state_dict(cfg, seed, variant)
-    m = DINOSeg(head="mlp", n_blocks=n_blocks, n_classes=n_classes, arch=arch)
+    m = DINOSeg(head=head, n_blocks=n_blocks, n_classes=n_classes, arch=arch)
     m.load_state_dict(sd, strict=True)
     return m.to("cuda:0"), cfg, sd
 
@@ -63,7 +63,8 @@ def _model(arch, n_blocks, seed, variant, n_classes=7):
 def _case(name):
     gd = load_golden(name)
     meta = gd["meta"]
-    m, cfg, sd = _model(meta["arch"], meta["n_blocks"], meta["seed"], meta["variant"], meta["n_classes"])
+    m, cfg, sd = _model(meta["arch"], meta["n_blocks"], meta["seed"], meta["variant"], meta["n_classes"],
+                        meta.get("head", "mlp"))
     x = synthetic.make_frames(meta["batch"], meta["res"], meta["seed"])
     return gd, meta, m, cfg, sd, x
 
@@ -85,7 +86,9 @@ def _compare_logprobs(tag, lp, ref, variant):
     mean_abs = float(err.mean())
     _record(case=tag, max_abs=max_abs, mean_abs=mean_abs, range=rng, rel_to_range=rel, variant=variant)
     if variant == "reference_init":
-        assert max_abs <= TOL_ABS_REFINIT, (tag, max_abs)
+        # absolute bar for the near-uniform log-probs of the MLP head (range < 1); scaled with the range for heads
+        # whose log-probs spread further (the 'linear' head: range ~4)
+        assert max_abs <= TOL_ABS_REFINIT * max(1.0, rng), (tag, max_abs, rng)
     else:
         assert rel <= TOL_REL_TRAINED, (tag, max_abs, rng)
     return max_abs

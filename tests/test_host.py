@@ -109,6 +109,11 @@ def test_load_from_checkpoint_roundtrip(tmp_path):
 def test_unsupported_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
         DINOSeg(head="mlp", backbone="cnn1")
+    with pytest.raises(ValueError):
+        DINOSeg(head="conv")
+    lin = DINOSeg(head="linear", n_classes=5)          # reference default head (pl_torch_modules.py:145, :127-138)
+    assert sorted(k for k in lin.state_dict() if k.startswith("clf.")) == ["clf.layer_1.bias", "clf.layer_1.weight"]
+    assert lin.state_dict()["clf.layer_1.weight"].shape == (5, 384)
     with pytest.raises(NotImplementedError):
         DINOSeg(head="mlp").fit()
 

@@ -19,7 +19,7 @@ TOL = 2e-5
 def _case(name):
     gd = load_golden(name)
     m = gd["meta"]
-    cfg = synthetic.make_config(m["arch"], m["n_blocks"], m["n_classes"])
+    cfg = synthetic.make_config(m["arch"], m["n_blocks"], m["n_classes"], head=m.get("head", "mlp"))
     sd = synthetic.init_state_dict(cfg, m["seed"], m["variant"])
     x = synthetic.make_frames(m["batch"], m["res"], m["seed"])
     return gd, m, cfg, sd, x
