@@ -1051,6 +1051,27 @@ int dinoseg_debug_set_attn_timing(long long* dev_ptr) {
 #endif
 }
 
+int dinoseg_cls_attention(dinoseg_t* h, const float* frames, int batch, float* attn, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!h) return -1;
+  if (h->res == 0) DSG_FAIL(h, "dinoseg_cls_attention: call dinoseg_set_resolution first");
+  if (!frames || !attn || batch <= 0 || !workspace) DSG_FAIL(h, "dinoseg_cls_attention: bad arguments");
+  if (h->cfg.n_blocks < 1) DSG_FAIL(h, "dinoseg_cls_attention: the model has no transformer block");
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  if (bind_workspace(h, h->user, workspace, workspace_bytes, batch) != 0) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // run the path up to the qkv GEMM of the last kept block, then softmax(q_cls k^T) per head
+  const int saved = h->debug_stop;
+  h->debug_stop = 2 + 3 * (h->cfg.n_blocks - 1);
+  const int rc = forward_impl(h, h->user, frames, nullptr, nullptr, batch, nullptr, nullptr, nullptr, s);
+  h->debug_stop = saved;
+  if (rc != 0) return rc;
+  dim3 grid(h->cfg.num_heads, batch);
+  cls_attention_kernel<<<grid, 256, 0, s>>>(h->user.qkv, attn, h->Ntok, h->cfg.embed_dim, h->cfg.num_heads);
+  DSG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
   if (!h) return -1;
   if (on && !(h->cfg.embed_dim == MLP_D && h->cfg.mlp_hidden == MLP_HID))

@@ -389,6 +389,73 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logprobs, uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------
+// CLS-query attention of one block: out[b, h, j] = softmax_j( q_cls(b,h) . k_j(b,h) )      (q pre-scaled by dh^-0.5)
+// = row 0 of the attention matrix VisionTransformer.get_last_selfattention returns (reference
+// vision_transformer.py:273-280, :85-101), the only row its caller uses (visualize_attention.py:46-54).
+// qkv: [B, N, 3D] bf16 as written by the qkv GEMM.  One CTA per (b, h); N x 64 dot products are nothing next to
+// the hot path, so this is a plain block-reduction kernel.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ out, int N, int D, int H) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const __nv_bfloat16* base = qkv + size_t(b) * N * 3 * D;
+  __shared__ float sq[64];
+  __shared__ float red[8];
+  __shared__ float bcast;
+  if (threadIdx.x < 64) sq[threadIdx.x] = __bfloat162float(base[h * 64 + threadIdx.x]);   // token 0 = cls, q part
+  __syncthreads();
+  float* o = out + (size_t(b) * H + h) * N;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const uint4* kp = reinterpret_cast<const uint4*>(base + size_t(j) * 3 * D + D + h * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = __ldg(kp + c);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc = fmaf(sq[c * 8 + 2 * e], __uint_as_float(w[e] << 16), acc);
+        acc = fmaf(sq[c * 8 + 2 * e + 1], __uint_as_float(w[e] & 0xffff0000u), acc);
+      }
+    }
+    o[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float e = expf(o[j] - mx);
+    o[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) o[j] *= inv;
+}
+
+// ---------------------------------------------------------------------------------------
 // Nearest-neighbour block replication == np.kron(low_res, ones((p,p), int))
 // (reference pl_torch_modules.py:297-298): out[b][y][x] = low[b][y/p][x/p], int64.
 // ---------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@ import io
 import pickle
 import types
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -71,10 +72,20 @@ class _Backbone(nn.Module):
         self.pos_embed = nn.Parameter(torch.zeros(1, n_pos + 1, dim))
         self.blocks = nn.ModuleList([_Block(dim, hidden) for _ in range(n_blocks)])
         self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self._owner = None            # weakref to the DINOSeg that executes this backbone
         # reference init (vision_transformer.py:188-200); Conv2d keeps its default init
         nn.init.trunc_normal_(self.pos_embed, std=.02)
         nn.init.trunc_normal_(self.cls_token, std=.02)
         self.apply(self._init_weights)
+
+    def get_last_selfattention(self, x):
+        """Reference vision_transformer.py:273-280 returns the last block's attention [B, H, N, N]; its only caller
+        (visualize_attention.py:46-54) reads the CLS row `[0, :, 0, 1:]`.  Here only that row is materialised:
+        the result has shape [B, H, 1, N] (the full matrix is 311 MB per frame at 480 px and is never formed)."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError("backbone is not attached to a DINOSeg model")
+        return owner.cls_attention(x).unsqueeze(2)
 
     @staticmethod
     def _init_weights(m):
@@ -177,6 +188,7 @@ class DINOSeg(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
 
+        self.dino._owner = weakref.ref(self)
         self._handle = None
         self._handle_device = None
         self._fingerprint = None
@@ -335,6 +347,24 @@ class DINOSeg(nn.Module):
                                  ws.data_ptr(), ws.numel(), self._stream())
         self._check(rc, "dinoseg_forward")
         return lp, low, lab
+
+    @torch.no_grad()
+    def cls_attention(self, x):
+        """Attention of the CLS query in the last kept block: [B, H, N] fp32 (see _Backbone.get_last_selfattention)."""
+        lib = self._ensure_handle()
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise ValueError(f"expected frames of shape [B,3,r,r], got {tuple(x.shape)}")
+        x = x.to(self.device).contiguous().float()
+        b, res = int(x.shape[0]), int(x.shape[2])
+        self._ensure_resolution(lib, res)
+        ws = self._ensure_workspace(lib, b)
+        n = (res // 8) ** 2 + 1
+        heads = ARCHS[self.arch]["num_heads"]
+        out = torch.empty((b, heads, n), dtype=torch.float32, device=self.device)
+        rc = lib.dinoseg_cls_attention(self._handle, x.data_ptr(), b, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       self._stream())
+        self._check(rc, "dinoseg_cls_attention")
+        return out
 
     def forward(self, x):
         """pl_torch_modules.py:239-256: [B,3,r,r] -> per-patch log-probabilities [B*P, C]."""

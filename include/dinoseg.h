@@ -97,6 +97,12 @@ int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames_u8, int bat
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 
+/* CLS-query attention of the last kept block: attn [batch, heads, N] fp32 = softmax(q_cls k^T * dh^-0.5) per head,
+ * i.e. row 0 of what VisionTransformer.get_last_selfattention returns (vision_transformer.py:273-280) — the only
+ * row its caller reads (visualize_attention.py:46-54).  frames: device fp32 [batch,3,r,r]. */
+int dinoseg_cls_attention(dinoseg_t* h, const float* frames, int batch, float* attn, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Output side of predict() on given log-probs: argmax (first max wins, NaN counts as max)
  * then p x p block replication.  Bit-exact w.r.t. torch.argmax + np.kron.
  * (pl_torch_modules.py:295-298).  rows = batch*g*g. */

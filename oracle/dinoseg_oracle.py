@@ -157,6 +157,20 @@ def backbone(sd: dict, cfg: dict, x: torch.Tensor, stages: dict | None = None) -
     return F.layer_norm(t, (d,), sd["dino.norm.weight"], sd["dino.norm.bias"], cfg["ln_eps"])
 
 
+@torch.no_grad()
+def last_selfattention_cls(sd: dict, cfg: dict, x: torch.Tensor) -> torch.Tensor:
+    """Row 0 (CLS query) of VisionTransformer.get_last_selfattention (vision_transformer.py:273-280): [B, H, N]."""
+    t = prepare_tokens(sd, x)
+    nb = cfg["n_blocks"]
+    for i in range(nb - 1):
+        t = block(sd, i, t, cfg["num_heads"], cfg["ln_eps"])
+    p = f"dino.blocks.{nb - 1}."
+    d = t.shape[-1]
+    y = F.layer_norm(t, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], cfg["ln_eps"])
+    _, attn = attention(sd, p + "attn.", y, cfg["num_heads"], return_attn=True)
+    return attn[:, :, 0, :]
+
+
 def head(sd: dict, x: torch.Tensor) -> torch.Tensor:
     """MLP head, pl_torch_modules.py:117-124; 'linear' head (no layer_2 in the state_dict), :135-138."""
     if "clf.layer_2.weight" not in sd:

@@ -86,6 +86,8 @@ def run_case(plm, vt, name, arch, n_blocks, res, batch, variant, seed):
         blk0 = m.dino.blocks[0](tokens)
         normed = m.dino(x)
         pos = m.dino.interpolate_pos_encoding(tokens, res, res)[0].detach()
+        # CLS row of the last block's attention (vision_transformer.py:273-280), small cases only (N x N is materialised)
+        cls_attn = m.dino.get_last_selfattention(x)[:, :, 0, :].numpy().astype(np.float32) if res <= 240 else np.zeros(0, np.float32)
     low = torch.argmax(lp, dim=-1).cpu().numpy().reshape(batch, g, g)
     p = 480 // g
     high = np.stack([np.kron(low[b], np.ones((p, p), dtype=int)) for b in range(batch)])
@@ -105,6 +107,7 @@ def run_case(plm, vt, name, arch, n_blocks, res, batch, variant, seed):
         tok_rows=tokens[:, rows].numpy().astype(np.float32),
         blk0_rows=blk0[:, rows].numpy().astype(np.float32),
         norm_rows=normed[:, rows].numpy().astype(np.float32),
+        cls_attn=cls_attn,
     )
     hist = np.bincount(low.reshape(-1), minlength=n_classes).tolist()
     print(f"{name}: logprobs {tuple(lp.shape)} range [{lp.min():.3f},{lp.max():.3f}] label hist {hist}")

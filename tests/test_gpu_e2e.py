@@ -275,6 +275,25 @@ def test_gpu_preprocessing_is_bit_exact(hw, res):
     assert (lab == low_f.cpu().numpy()).all()
 
 
+@pytest.mark.parametrize("name", ["s8_nb1_240_refinit", "s8_nb3_240_b2_trained", "b8_nb4_240_refinit"])
+def test_cls_attention_against_reference(name):
+    """model.dino.get_last_selfattention(x)[b, :, 0, :] (the row visualize_attention.py:46-54 reads) vs the reference's
+    (vision_transformer.py:273-280): rows are probability vectors; max error <= 2 % of the largest probability
+    (6 % for the peaked attention of the 'trained_like' stress weights, whose bf16 q/k rounding moves the logits by ~0.02)."""
+    gd, meta, m, cfg, sd, x = _case(name)
+    att = m.dino.get_last_selfattention(x.cuda())
+    torch.cuda.synchronize()
+    n = (meta["res"] // 8) ** 2 + 1
+    assert tuple(att.shape) == (meta["batch"], cfg["num_heads"], 1, n)
+    got = att[:, :, 0, :].cpu().numpy()
+    ref = gd["cls_attn"]
+    assert np.abs(got.sum(-1) - 1.0).max() <= 1e-5
+    err = float(np.abs(got - ref).max())
+    _record(case=name, cls_attn_max_abs=err, cls_attn_ref_max=float(ref.max()))
+    tol = 2e-2 if meta["variant"] == "reference_init" else 6e-2
+    assert err <= tol * float(ref.max()), (err, float(ref.max()))
+
+
 def test_fused_mlp_matches_unfused_path():
     """ViT-S runs fc1 -> GELU -> fc2 in one fused kernel; the unfused LN / fc1 / fc2 GEMM path (what ViT-B uses)
     must give the same log-probs up to bf16 rounding noise, and both must match the oracle."""

@@ -114,3 +114,12 @@ def test_preprocessing_oracle_matches_cv2_and_transforms(hw, res):
     assert (P.resize_linear_u8(img, res) == ref).all()
     t = get_transforms(res)(image=img)["image"].numpy()
     assert np.array_equal(P.preprocess(img, res), t)
+
+
+@pytest.mark.parametrize("name", ["s8_nb1_240_refinit", "s8_nb3_240_b2_trained", "b8_nb4_240_refinit"])
+def test_oracle_cls_attention_matches_reference(name):
+    """CLS row of VisionTransformer.get_last_selfattention (vision_transformer.py:273-280) as the reference computed it."""
+    gd, m, cfg, sd, x = _case(name)
+    got = O.last_selfattention_cls(sd, cfg, x).numpy()
+    assert got.shape == gd["cls_attn"].shape
+    assert np.abs(got - gd["cls_attn"]).max() <= 1e-6
