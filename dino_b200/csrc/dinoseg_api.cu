@@ -896,7 +896,21 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
     if (e == cudaSuccess) *cap = need;
     return e;
   };
-  const int nchunks = (batch + chunk - 1) / chunk;
+  // chunk plan: a SHORT first chunk (its H2D copy is the pipeline fill that nothing overlaps) and a short last one
+  // (its D2H copy is the drain), full chunks in between
+  std::vector<int> plan;
+  if (batch <= chunk) {
+    plan.push_back(batch);
+  } else {
+    int rest = batch;
+    const int rem = batch % chunk;
+    const int first = rem ? rem : chunk / 2;
+    plan.push_back(first);
+    rest -= first;
+    while (rest > chunk) { plan.push_back(chunk); rest -= chunk; }
+    plan.push_back(rest);           // = chunk, or the other half of a split chunk when chunk divides batch
+  }
+  const int nchunks = int(plan.size());
   const int nlanes = nchunks < dinoseg::kLanes ? nchunks : dinoseg::kLanes;
   for (int k = 0; k < nlanes; ++k) {
     HostLane& l = h->lanes[k];
@@ -913,10 +927,11 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
   // lanes start after whatever the caller queued on its stream
   DSG_CUDA(h, cudaEventRecord(h->host_start, s));
   for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamWaitEvent(h->lanes[k].stream, h->host_start, 0));
-  for (int c = 0; c < nchunks; ++c) {
+  int f0 = 0;
+  for (int c = 0; c < nchunks; f0 += plan[c], ++c) {
     HostLane& l = h->lanes[c % nlanes];
-    const int f0 = c * chunk;
-    const int nb = (batch - f0) < chunk ? (batch - f0) : chunk;
+    const int nb = plan[c];
+    if (nb <= 0) continue;
     DSG_CUDA(h, cudaMemcpyAsync(l.frames, static_cast<const uint8_t*>(host_frames) + size_t(f0) * frame_bytes,
                                 size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, l.stream));
     if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
