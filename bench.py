@@ -216,6 +216,7 @@ def main():
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound_cores = D.bind_to_gpu_cpus(local_rank) if world > 1 else 0   # NUMA-local host buffers for the e2e copies
     peaks, peaks_src = load_peaks()
 
     cfg = synthetic.make_config(args.arch, args.n_blocks, 7)
@@ -344,7 +345,7 @@ def main():
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "weights": f"random init ({args.variant})",
-                   "parallelism": f"replicas x{world} (frames sharded, no collective)",
+                   "parallelism": f"replicas x{world} (frames sharded, no collective)", "host_cores_bound_per_rank": bound_cores,
                    "l2": "inputs+workspace per step (>1.5 GB) exceed the 126 MB L2; no explicit flush",
                    "arithmetic": "bf16 tensor-core operands, fp32 accumulate / residual stream / LN / softmax / GELU"},
         "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches_per_step * args.steps),

@@ -30,6 +30,26 @@ def init(backend: str | None = None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_cpus(local_rank: int) -> int:
+    """Pin this process to the host cores NVML reports as local to GPU `local_rank` (its NUMA node), so that
+    the pinned staging buffers and the copy threads sit next to the GPU's PCIe root.  Returns the number of cores
+    the process may run on afterwards (0 = left unchanged: NVML or sched_setaffinity unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {w * 64 + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of `total` units for `rank` (sizes differ by at most one)."""
     base, rem = divmod(total, world)
