@@ -57,6 +57,8 @@ SIGNATURES = {
     "dinoseg_debug_set_attn_timing": (C.c_int, [C.c_void_p]),
     "dinoseg_op_mlp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p]),
+    "dinoseg_op_mlp_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_void_p]),
     "dinoseg_set_fused_mlp": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_float, C.c_void_p]),

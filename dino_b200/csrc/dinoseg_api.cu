@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -122,22 +123,41 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 constexpr int kAttnStages = 4;
 long long* g_attn_timing = nullptr;   // debug: device buffer for the DSG_*_TIMING builds
 
-cudaError_t launch_mlp_fused(const CUtensorMap& a, const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& x, const MlpParams& p,
-                             int num_sms, cudaStream_t s) {
-  static bool attr[64] = {};
+// The weight tensor maps come in two flavours: full 128-row granules (plain kernel) and 64-row half granules (cluster
+// kernel: each CTA of a cta_group::2 pair holds one half of the B operand).
+cudaError_t launch_mlp_fused(const CUtensorMap& a, const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& x,
+                             const MlpParams& p, int num_sms, bool pair, cudaStream_t s) {
+  static bool attr[64][2] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MLP_SMEM));
+  if (!attr[dev & 63][pair]) {
+    cudaError_t e = pair ? cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MLP_SMEM))
+                              : cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MLP_SMEM));
     if (e != cudaSuccess) return e;
-    attr[dev & 63] = true;
+    attr[dev & 63][pair] = true;
   }
-  const int m_blocks = (p.M + MLP_BM - 1) / MLP_BM;
-  const int grid = m_blocks < num_sms ? m_blocks : num_sms;
   MlpParams pp = p;
   pp.timing = g_attn_timing;
-  mlp_fused_kernel<<<grid, MLP_THREADS, MLP_SMEM, s>>>(a, w1, w2, x, pp);
-  return cudaGetLastError();
+  const int m_blocks = (p.M + MLP_BM - 1) / MLP_BM;
+  if (!pair) {
+    const int grid = m_blocks < num_sms ? m_blocks : num_sms;
+    mlp_fused_kernel<false><<<grid, MLP_THREADS, MLP_SMEM, s>>>(a, w1, w2, x, pp);
+    return cudaGetLastError();
+  }
+  const int pairs = (m_blocks + 1) / 2;
+  const int max_pairs = num_sms / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(MLP_THREADS);
+  cfg.dynamicSmemBytes = MLP_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, mlp_fused_kernel<true>, a, w1, w2, x, pp);
 }
 
 constexpr int kLinPitch = 16;    // row pitch (floats) of the 'linear' head's logits buffer (n_classes <= 16)
@@ -274,6 +294,7 @@ struct BlockW {
   float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
   CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
   CUtensorMap tm_fc1_g, tm_fc2_g;   // 128-row granule views for the fused MLP kernel
+  CUtensorMap tm_fc1_h, tm_fc2_h;   // 64-row half granules (CTA-pair variant)
 };
 
 struct WeightSlot {
@@ -343,7 +364,8 @@ struct dinoseg {
 
   int debug_stop = 0;
   int launches = 0;
-  bool fused_mlp = false;           // D = 384 / hidden = 1536: fused LN2 -> fc1 -> GELU -> fc2 kernel
+  bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
+  bool mlp_pair = false;       // ... as CTA pairs (cta_group::2), half the weights per SM
 
   // optional per-kernel-kind timing (cudaEvents around every launch of a forward)
   bool profile = false;
@@ -500,6 +522,11 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->cfg = *cfg;
   h->device = device;
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
+  if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
+    const int m = atoi(mode);
+    h->fused_mlp = h->fused_mlp && m != 0;
+    h->mlp_pair = h->fused_mlp && m == 2;
+  }
   h->num_sms = prop.multiProcessorCount;
   const int D = cfg->embed_dim, HID = cfg->mlp_hidden, G0 = cfg->pos_grid, C = cfg->n_classes;
   const bool linear_head = cfg->head_kind == 1;          // reference pl_torch_modules.py:127-138: Linear(D, C)
@@ -555,6 +582,8 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc1_g, b.fc1_w, HID, D, D, 128);
     ok &= make_tmap_2d(&b.tm_fc2_g, b.fc2_w, D, HID, HID, 128);
+    ok &= make_tmap_2d(&b.tm_fc1_h, b.fc1_w, HID, D, D, 64);
+    ok &= make_tmap_2d(&b.tm_fc2_h, b.fc2_w, D, HID, HID, 64);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed for block weights"; rc = -1; }
   }
   if (rc == 0) {
@@ -785,7 +814,9 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       MlpParams p{};
       p.M = M; p.x = w.x; p.b1 = b.fc1_b; p.b2 = b.fc2_b;
       LaunchScope ls(h, K_MLP_FUSED, s);
-      DSG_CUDA(h, launch_mlp_fused(w.tm_abuf, b.tm_fc1_g, b.tm_fc2_g, w.tm_x_out, p, sms, s)); ++n;
+      if (h->mlp_pair) DSG_CUDA(h, launch_mlp_fused(w.tm_abuf, b.tm_fc1_h, b.tm_fc2_h, w.tm_x_out, p, sms, true, s));
+      else DSG_CUDA(h, launch_mlp_fused(w.tm_abuf, b.tm_fc1_g, b.tm_fc2_g, w.tm_x_out, p, sms, false, s));
+      ++n;
     } else {
       { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
       {
@@ -1092,24 +1123,31 @@ int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
   if (on && !(h->cfg.embed_dim == MLP_D && h->cfg.mlp_hidden == MLP_HID))
     DSG_FAIL(h, "the fused MLP kernel needs embed_dim 384 and mlp_hidden 1536");
   h->fused_mlp = on != 0;
+  h->mlp_pair = on == 2;
   return 0;
 }
 
 int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                    const float* b2, int M, void* stream) {
+  return dinoseg_op_mlp_ex(x, A_bf16, W1_bf16, b1, W2_bf16, b2, M, 0, stream);
+}
+
+int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                      const float* b2, int M, int pair, void* stream) {
   if (!x || !A_bf16 || !W1_bf16 || !b1 || !W2_bf16 || !b2 || M <= 0) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   CUtensorMap ta, t1, t2, tx;
+  const uint32_t wrows = pair ? 64 : 128;
   bool ok = make_tmap_gemm_a(&ta, A_bf16, M, 1, MLP_D);
-  ok &= make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, 128);
-  ok &= make_tmap_2d(&t2, W2_bf16, MLP_D, MLP_HID, MLP_HID, 128);
+  ok &= make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, wrows);
+  ok &= make_tmap_2d(&t2, W2_bf16, MLP_D, MLP_HID, MLP_HID, wrows);
   ok &= make_tmap_gemm_out(&tx, x, true, MLP_D, M, 1, MLP_D);
   if (!ok) return -2;
   MlpParams p{};
   p.M = M; p.x = x; p.b1 = b1; p.b2 = b2;
-  return launch_mlp_fused(ta, t1, t2, tx, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+  return launch_mlp_fused(ta, t1, t2, tx, p, sms, pair != 0, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {

@@ -76,6 +76,16 @@ __device__ __forceinline__ float2 gelu_erf_x2(float2 x) {
   return ffma2(ax, d, hx);
 }
 
+// PAIR = true: the kernel runs as CTA pairs (clusters of two, tcgen05 cta_group::2).  A pair owns two neighbouring row
+// blocks (256 rows); every MMA is one M = 256 instruction issued by the leader CTA (cluster rank 0) and executed by both
+// SMs, each on its own 128 rows of A / G and its own accumulators, with the B operand (a weight granule) SPLIT between
+// the two CTAs' shared memories: each CTA streams only half of the weights (64 of the 128 rows of every granule).
+// The kernel is bound by the L2 -> SM delivery of the weights (2.36 MB per row block at ~42 B/clk/SM); the pair halves
+// it, and the ring holds 8 half granules instead of 4 whole ones.  (A TMA-multicast variant without cta_group::2 -
+// same bytes delivered to every SM - measured no gain at all.)
+// Barriers: everything the MMA issuer waits on lives in the leader CTA and collects both CTAs' arrivals (remote
+// mbarrier arrives, TMA complete_tx from the peer's loads); everything it signals is a multicast commit to both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX, const MlpParams p) {
@@ -89,46 +99,63 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;                               // [6][16 KB]  LN2(x) bf16 row block (TMA), K-major SW128
   uint8_t* sG = sA + size_t(MLP_KB) * MLP_GRAN;     // [2 k-blocks][16 KB]  gelu(fc1) chunk, A operand of fc2
   uint8_t* sS = sG + 2 * MLP_GRAN;                  // [2][16 KB]  staging of the output warps
-  uint8_t* sR = sS + 2 * MLP_GRAN;                  // [4][16 KB]  weight granule ring
+  uint8_t* sR = sS + 2 * MLP_GRAN;                  // [4][16 KB]  weight granule ring  (PAIR: [8][8 KB] half granules)
+  constexpr int RING = PAIR ? 2 * MLP_RING : MLP_RING;
+  constexpr uint32_t SLOT = PAIR ? MLP_GRAN / 2 : MLP_GRAN;
+  constexpr uint32_t NCTA = PAIR ? 2 : 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sR + size_t(MLP_RING) * MLP_GRAN);
-  uint64_t* w_full = bars;                          // MLP_RING
-  uint64_t* w_empty = w_full + MLP_RING;            // MLP_RING
-  uint64_t* a_full = w_empty + MLP_RING;            // 1 (TMA transaction barrier: 6 granules)
+  uint64_t* w_full = bars;                          // RING
+  uint64_t* w_empty = w_full + 2 * MLP_RING;        // RING
+  uint64_t* a_full = w_empty + 2 * MLP_RING;        // 1 (TMA transaction barrier: 6 granules per CTA)
   uint64_t* a_empty = a_full + 1;                   // 1 (commit after the last MMA1 of a row block)
   uint64_t* acc1_full = a_empty + 1;                // 1 (commit)
-  uint64_t* acc1_empty = acc1_full + 1;             // 1 (8 arrivals)
-  uint64_t* g_full = acc1_empty + 1;                // 1 (256 arrivals)
+  uint64_t* acc1_empty = acc1_full + 1;             // 1 (8 arrivals per CTA)
+  uint64_t* g_full = acc1_empty + 1;                // 1 (8 arrivals per CTA)
   uint64_t* g_empty = g_full + 1;                   // 1 (commit after MMA2 of the chunk)
   uint64_t* acc2_full = g_empty + 1;                // 1 (commit after the last MMA2)
-  uint64_t* acc2_empty = acc2_full + 1;             // 1 (4 arrivals)
-  uint64_t* add_bar = acc2_empty + 1;               // 2 (x chunks landed in staging)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 2);
+  uint64_t* acc2_empty = acc2_full + 1;             // 1 (4 arrivals per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int m_blocks = (p.M + MLP_BM - 1) / MLP_BM;
-  const int my_blocks = int(blockIdx.x) < m_blocks ? (m_blocks - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+  // plain: row blocks bid, bid + G, ...; PAIR: cluster k takes the block pairs k, k + G/2, ... and rank r the r-th of
+  // a pair (a block index past the end is harmless: TMA zero-fills its loads and clips its stores)
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
+  const int units = PAIR ? (m_blocks + 1) / 2 : m_blocks;
+  const int unit0 = PAIR ? int(blockIdx.x) / 2 : int(blockIdx.x);
+  const int unit_stride = PAIR ? int(gridDim.x) / 2 : int(gridDim.x);
+  const int my_blocks = unit0 < units ? (units - 1 - unit0) / unit_stride + 1 : 0;
+  auto block_row0 = [&](int bi) { return ((unit0 + bi * unit_stride) * (PAIR ? 2 : 1) + int(cta_rank)) * MLP_BM; };
+  // arrive on a barrier of the leader CTA (the MMA issuer's side)
+  auto arrive_leader = [&](uint64_t* bar) {
+    if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar, 0));
+    else mbar_arrive(bar);
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
-    for (int s = 0; s < MLP_RING; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < RING; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     mbar_init(acc1_full, 1);
-    mbar_init(acc1_empty, 8);
-    mbar_init(g_full, 256);
+    mbar_init(acc1_empty, 8 * NCTA);
+    mbar_init(g_full, 8 * NCTA);
     mbar_init(g_empty, 1);
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 4);
-    for (int s = 0; s < 2; ++s) mbar_init(&add_bar[s], 1);
+    mbar_init(acc2_empty, 4 * NCTA);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -137,29 +164,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ---------------- TMA producer ----------------
       // per row block: A (6 granules, own buffer) | W1(0) | W1(1) W2(0) | W1(2) W2(1) | ... | W2(11)  through the ring
       uint32_t rc = 0;
-      auto load_w1 = [&](int c) {
-        for (int kb = 0; kb < MLP_KB; ++kb, ++rc) {
-          const int s = rc % MLP_RING;
-          mbar_wait(&w_empty[s], ((rc / MLP_RING) & 1) ^ 1);
-          mbar_expect_tx(&w_full[s], MLP_GRAN);
-          tma_load_2d(sR + size_t(s) * MLP_GRAN, &tmW1, &w_full[s], kb * 64, c * MLP_CH);   // W1[c*128.., kb*64..]
+      // one ring slot: wait until the MMAs that read it have retired (both SMs), then fetch the next granule - in PAIR
+      // mode my 64-row half of it, completing on the leader's barrier (which expects both halves)
+      auto load_gran = [&](const CUtensorMap* tm, int c0, int row0) {
+        const int s = rc % RING;
+        mbar_wait(&w_empty[s], ((rc / RING) & 1) ^ 1);
+        if constexpr (PAIR) {
+          if (cta_rank == 0) mbar_expect_tx(&w_full[s], 2 * SLOT);
+          tma_load_2d_pair(sR + size_t(s) * SLOT, tm, mapa_rank(&w_full[s], 0), c0, row0 + int(cta_rank) * 64);
+        } else {
+          mbar_expect_tx(&w_full[s], SLOT);
+          tma_load_2d(sR + size_t(s) * SLOT, tm, &w_full[s], c0, row0);
         }
+        ++rc;
+      };
+      auto load_w1 = [&](int c) {
+        for (int kb = 0; kb < MLP_KB; ++kb) load_gran(&tmW1, kb * 64, c * MLP_CH);               // W1[c*128.., kb*64..]
       };
       auto load_w2 = [&](int c) {
-        for (int kb = 0; kb < MLP_CH / 64; ++kb) {
-          for (int nt = 0; nt < MLP_D / 128; ++nt, ++rc) {
-            const int s = rc % MLP_RING;
-            mbar_wait(&w_empty[s], ((rc / MLP_RING) & 1) ^ 1);
-            mbar_expect_tx(&w_full[s], MLP_GRAN);
-            tma_load_2d(sR + size_t(s) * MLP_GRAN, &tmW2, &w_full[s], c * MLP_CH + kb * 64, nt * 128);
-          }
-        }
+        for (int kb = 0; kb < MLP_CH / 64; ++kb)
+          for (int nt = 0; nt < MLP_D / 128; ++nt) load_gran(&tmW2, c * MLP_CH + kb * 64, nt * 128);
       };
       auto load_a = [&](int bi) {
-        const int r0 = (int(blockIdx.x) + bi * int(gridDim.x)) * MLP_BM;
+        const int r0 = block_row0(bi);
         if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1);   // last MMA1 of the previous block has read A
-        mbar_expect_tx(a_full, MLP_KB * MLP_GRAN);
-        for (int kb = 0; kb < MLP_KB; ++kb) tma_load_3d(sA + size_t(kb) * MLP_GRAN, &tmA, a_full, kb * 64, r0, 0);
+        if constexpr (PAIR) {
+          if (cta_rank == 0) mbar_expect_tx(a_full, 2 * MLP_KB * MLP_GRAN);
+          const uint32_t bar = mapa_rank(a_full, 0);
+          for (int kb = 0; kb < MLP_KB; ++kb) tma_load_3d_pair(sA + size_t(kb) * MLP_GRAN, &tmA, bar, kb * 64, r0, 0);
+        } else {
+          mbar_expect_tx(a_full, MLP_KB * MLP_GRAN);
+          for (int kb = 0; kb < MLP_KB; ++kb) tma_load_3d(sA + size_t(kb) * MLP_GRAN, &tmA, a_full, kb * 64, r0, 0);
+        }
       };
       if (my_blocks > 0) load_a(0);
       for (int bi = 0; bi < my_blocks; ++bi) {
@@ -172,29 +208,41 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (cta_rank == 0 && elect_one()) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, 128, 0);
+      auto wait = [&](uint64_t* bar, uint32_t parity) {
+        if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) tc_commit_pair(bar, uint16_t(3));
+        else tc_commit(bar);
+      };
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if constexpr (PAIR) umma_ss_pair(d, ad, bd, idesc, acc);
+        else umma_ss(d, ad, bd, idesc, acc);
+      };
       uint32_t rc = 0;        // ring counter (same order as the producer)
       uint32_t c1 = 0;        // acc1 uses so far
       uint32_t gc = 0;        // G uses so far
       MLP_T_DECL;
       auto wait_gran = [&]() -> uint32_t {
-        const int s = rc % MLP_RING;
+        const int s = rc % RING;
         MLP_T(7);
-        mbar_wait(&w_full[s], (rc / MLP_RING) & 1);
+        wait(&w_full[s], (rc / RING) & 1);
         MLP_T(0);
         tc_fence_after();
-        return smem_u32(sR + size_t(s) * MLP_GRAN);
+        return smem_u32(sR + size_t(s) * SLOT);
       };
       auto free_gran = [&]() {
-        tc_commit(&w_empty[rc % MLP_RING]);
+        commit(&w_empty[rc % RING]);
         ++rc;
       };
       auto mma1 = [&](int c) {
         // acc1 = A . W1[c]^T ; the GELU warps must have pulled the previous acc1 into registers
         MLP_T(7);
-        mbar_wait(acc1_empty, (c1 & 1) ^ 1);
+        wait(acc1_empty, (c1 & 1) ^ 1);
         MLP_T(1);
         tc_fence_after();
         for (int kb = 0; kb < MLP_KB; ++kb) {
@@ -203,17 +251,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t bdesc = umma_desc_sw128(sw);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ss(tmem_base + ACC1_COL, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            mma(tmem_base + ACC1_COL, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), (kb | k) != 0);
           free_gran();
         }
-        tc_commit(acc1_full);
+        commit(acc1_full);
         ++c1;
-        if (c == MLP_NCH - 1) tc_commit(a_empty);   // the next row block's A may be loaded
+        if (c == MLP_NCH - 1) commit(a_empty);   // the next row block's A may be loaded
       };
       auto mma2 = [&](int c, bool first_of_block) {
         // acc2 += G . W2[:, c]^T
         MLP_T(7);
-        mbar_wait(g_full, gc & 1);
+        wait(g_full, gc & 1);
         MLP_T(2);
         tc_fence_after();
         for (int kb = 0; kb < MLP_CH / 64; ++kb) {
@@ -223,18 +271,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t bdesc = umma_desc_sw128(sw);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tmem_base + ACC2_COL + uint32_t(nt * 128), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
-                      (!first_of_block || kb != 0 || k != 0) ? 1u : 0u);
+              mma(tmem_base + ACC2_COL + uint32_t(nt * 128), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2),
+                  (!first_of_block || kb != 0 || k != 0) ? 1u : 0u);
             free_gran();
           }
         }
-        tc_commit(g_empty);
+        commit(g_empty);
         ++gc;
         (void)c;
       };
       for (int bi = 0; bi < my_blocks; ++bi) {
         MLP_T(7);
-        mbar_wait(a_full, bi & 1);                  // LN2(x) row block has landed
+        wait(a_full, bi & 1);                       // LN2(x) row block has landed
         MLP_T(3);
         tc_fence_after();
         for (int i = 0; i < MLP_NCH + MLP_LAG; ++i) {
@@ -243,14 +291,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int c = i - MLP_LAG;
             if (c == 0) {
               MLP_T(7);
-              mbar_wait(acc2_empty, (bi & 1) ^ 1);  // the output warps have drained the previous block's acc2
+              wait(acc2_empty, (bi & 1) ^ 1);       // the output warps have drained the previous block's acc2
               MLP_T(4);
               tc_fence_after();
             }
             mma2(c, c == 0);
           }
         }
-        tc_commit(acc2_full);
+        commit(acc2_full);
       }
       MLP_T_DUMP(0);
     }
@@ -279,7 +327,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc1_empty);     // MMA1 of the next chunk may overwrite acc1
+        if (lane == 0) arrive_leader(acc1_empty);   // MMA1 of the next chunk may overwrite acc1
         const float* b1 = p.b1 + c * MLP_CH + half * 64;
         uint4 q[8];
 #pragma unroll
@@ -301,16 +349,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(dst + ((k ^ (row & 7)) << 4)) = q[k];
         fence_proxy_async_smem();
-        mbar_arrive(g_full);
+        __syncwarp();
+        if (lane == 0) arrive_leader(g_full);
         MLP_T(4);
       }
     }
     if (threadIdx.x == 64) { MLP_T_DUMP(1); }
   } else {
     // ---------------- output warps (4): x += acc2 + b2, 12 chunks of 32 fp32 columns ----------------
-    // x chunks are TMA-loaded into a swizzled staging buffer (one chunk ahead, the first one long before acc2
-    // is complete), the accumulator + bias is added in place and the buffer is TMA-stored back.
-    // (Reading x with plain loads, one row per thread, measured 25 % slower for the whole kernel.)
+    // acc2 + b2 goes through a swizzled staging buffer into a TMA reduce-add on x: the fp32 add happens at L2 (one
+    // add per element, so the result is the same single rounding as x + (acc2 + b2) in registers) and x is never
+    // loaded into the SM.  Loading x chunks with TMA, adding in shared memory and storing back made this drain
+    // latency-bound (~1500 clk per chunk, one load in flight) and cost the MMA issuer ~14k clk per row block waiting
+    // for acc2; plain per-thread loads of x were 25 % slower still.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const bool leader = threadIdx.x == 320;
@@ -318,16 +369,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int NCH = MLP_D / 32;                 // 12
     uint32_t addc = 0;                              // staging chunks so far
     for (int bi = 0; bi < my_blocks; ++bi) {
-      const int r0 = (int(blockIdx.x) + bi * int(gridDim.x)) * MLP_BM;
-      auto issue_add = [&](int ch, uint32_t gidx) {
-        const int b = gidx & 1;
-        mbar_expect_tx(&add_bar[b], MLP_GRAN);
-        tma_load_3d(sS + size_t(b) * MLP_GRAN, &tmX, &add_bar[b], ch * 32, r0, 0);
-      };
-      if (leader) {
-        tma_store_wait_read<0>();
-        issue_add(0, addc);
-      }
+      const int r0 = block_row0(bi);
       mbar_wait(acc2_full, bi & 1);                 // every MMA2 of this block has retired
       tc_fence_after();
       for (int ch = 0; ch < NCH; ++ch, ++addc) {
@@ -344,31 +386,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ch == NCH - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc2_empty);   // the next block's MMA2 may overwrite acc2
+          if (lane == 0) arrive_leader(acc2_empty); // the next block's MMA2 may overwrite acc2
         }
         const float* b2 = p.b2 + ch * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(b2 + i));
-          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-        }
-        if (leader && ch + 1 < NCH) {
-          tma_store_wait_read<0>();                 // the store that last read the other buffer is done
-          issue_add(ch + 1, addc + 1);
-        }
-        mbar_wait(&add_bar[b], (addc >> 1) & 1);
+        // staging buffer b was last read by the reduce of chunk addc - 2: the leader waited for that read before the
+        // barrier of chunk addc - 1
         uint8_t* srow = sS + size_t(b) * MLP_GRAN + row * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float4* ptr = reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4));
-          float4 a = *ptr;
-          a.x += v[4 * k]; a.y += v[4 * k + 1]; a.z += v[4 * k + 2]; a.w += v[4 * k + 3];
-          *ptr = a;
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(b2 + 4 * k));
+          *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
+              make_float4(v[4 * k] + bv.x, v[4 * k + 1] + bv.y, v[4 * k + 2] + bv.z, v[4 * k + 3] + bv.w);
         }
         fence_proxy_async_smem();
+        if (leader) tma_store_wait_read<0>();       // the other buffer is free again
         named_bar_sync(2, 128);
         if (leader) {
-          tma_store_3d(&tmX, sS + size_t(b) * MLP_GRAN, ch * 32, r0, 0);
+          tma_reduce_add_3d(&tmX, sS + size_t(b) * MLP_GRAN, ch * 32, r0, 0);
           tma_store_commit();
         }
       }
@@ -378,7 +412,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (PAIR) cluster_sync_all();           // both CTAs are done with each other's barriers and TMEM
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace dsg

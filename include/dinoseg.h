@@ -144,7 +144,10 @@ int dinoseg_debug_set_attn_timing(long long* dev_ptr);
  * bf16: the fused transformer-MLP kernel (reference vision_transformer.py:135, :59-65) */
 int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                    const float* b2, int M, void* stream);
-/* switch between the fused MLP kernel (default for ViT-S) and the unfused LN / fc1 / fc2 kernels */
+/* the same kernel run by CTA pairs (tcgen05 cta_group::2, M = 256 per MMA, weights split between the two SMs) when pair != 0 */
+int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                      const float* b2, int M, int pair, void* stream);
+/* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel; 2: fused MLP kernel run by CTA pairs (cta_group::2) */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
                          float eps, void* stream);

@@ -303,10 +303,13 @@ def test_fused_mlp_matches_unfused_path():
     a = m(x).clone()
     assert lib.dinoseg_set_fused_mlp(m._handle, 0) == 0
     b = m(x).clone()
+    assert lib.dinoseg_set_fused_mlp(m._handle, 2) == 0     # CTA pairs (cta_group::2): same MMAs per row, same bits
+    d = m(x).clone()
     assert lib.dinoseg_set_fused_mlp(m._handle, 1) == 0
     c = m(x)
     torch.cuda.synchronize()
     assert torch.equal(a, c)
+    assert torch.equal(a, d)
     ref = O.forward(sd, cfg, x.cpu())
     rng = float(ref.max() - ref.min())
     assert (a - b).abs().max().item() <= 5e-3 * rng

@@ -121,7 +121,7 @@ def check_attention(name, B, N, H):
                    ref_absmax=scale, tol=tol, n_bad=int(bad.shape[0]), first_bad=first_bad)
 
 
-def check_mlp(name, M):
+def check_mlp(name, M, pair=0):
     """Fused fc1 -> GELU(erf) -> fc2 -> +x kernel (A = LayerNorm(x) in bf16) vs fp32 torch (bf16 operand rounding emulated for the
     reference's inputs only through the tolerance: 1 % of the output's max-abs)."""
     torch, L, lib = _imports()
@@ -140,7 +140,7 @@ def check_mlp(name, M):
     ref = x + F.linear(hid.to(torch.bfloat16).float(), W2.float(), b2)
     y = x.clone()
     A = ln.to(torch.bfloat16).contiguous()
-    rc = lib.dinoseg_op_mlp(_ptr(y), _ptr(A), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, None)
+    rc = lib.dinoseg_op_mlp_ex(_ptr(y), _ptr(A), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, pair, None)
     torch.cuda.synchronize()
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()
@@ -253,6 +253,9 @@ def _checks():
         "mlp_1block": lambda: check_mlp("mlp_1block", 128),
         "mlp_ragged": lambda: check_mlp("mlp_ragged", 901),
         "mlp_multi": lambda: check_mlp("mlp_multi", 148 * 128 * 2 + 77),
+        "mlp_pair_1block": lambda: check_mlp("mlp_pair_1block", 128, 1),
+        "mlp_pair_ragged": lambda: check_mlp("mlp_pair_ragged", 901, 1),
+        "mlp_pair_multi": lambda: check_mlp("mlp_pair_multi", 148 * 128 * 2 + 77, 1),
     }
 
 
@@ -261,7 +264,7 @@ def check_names():
         "layernorm_384", "layernorm_768", "posembed_30", "posembed_60", "posembed_28", "posembed_vitb_60", "im2col",
         "argmax_replicate", "argmax_replicate_odd", "gemm_tile", "gemm_k384", "gemm_qkv", "gemm_gelu",
         "gemm_resid_k1536", "gemm_patch", "gemm_head", "gemm_big", "attn_1tile", "attn_ragged_small", "attn_2tiles",
-        "attn_901", "attn_3601", "attn_vitb_901", "mlp_1block", "mlp_ragged", "mlp_multi",
+        "attn_901", "attn_3601", "attn_vitb_901", "mlp_1block", "mlp_ragged", "mlp_multi", "mlp_pair_1block", "mlp_pair_ragged", "mlp_pair_multi",
     ]
 
 

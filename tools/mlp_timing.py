@@ -16,7 +16,8 @@ EPI = ["-", "wait acc1_full", "ld + gelu", "wait g_empty", "write G", "-", "-", 
 def main():
     lib = C.CDLL(so)
     lib.dinoseg_debug_set_attn_timing.argtypes = [C.c_void_p]
-    lib.dinoseg_op_mlp.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    lib.dinoseg_op_mlp_ex.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]
+    mc = int(os.environ.get("DSG_MLP_MC", "0"))
     M = 64 * 3601
     dev = "cuda"
     x = torch.randn(M, 384, device=dev)
@@ -26,20 +27,20 @@ def main():
     timing = torch.zeros(148 * 2 * 8, dtype=torch.int64, device=dev)
     have = lib.dinoseg_debug_set_attn_timing(timing.data_ptr()) == 0
     A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
-    args = (x.data_ptr(), A.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, None)
+    args = (x.data_ptr(), A.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, mc, None)
     for _ in range(2):
-        lib.dinoseg_op_mlp(*args)
+        lib.dinoseg_op_mlp_ex(*args)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 1 if have else 5
     e0.record()
     for _ in range(reps):
-        lib.dinoseg_op_mlp(*args)
+        lib.dinoseg_op_mlp_ex(*args)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     blocks = ((M + 127) // 128) / 148.0
-    print(f"mlp_fused {ms:.3f} ms, {4.0 * M * 384 * 1536 / ms / 1e9:.0f} TFLOP/s, {ms * 1e-3 * 1.965e9 / blocks:.0f} clk per row block")
+    print(f"mlp_fused mc={mc} {ms:.3f} ms, {4.0 * M * 384 * 1536 / ms / 1e9:.0f} TFLOP/s, {ms * 1e-3 * 1.965e9 / blocks:.0f} clk per row block")
     if have:
         t = timing.view(148, 2, 8).double().cpu().mean(0)
         for role, names in ((0, MMA), (1, EPI)):
