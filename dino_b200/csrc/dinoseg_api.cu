@@ -120,7 +120,7 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 // -----------------------------------------------------------------------------------------
 // kernel launchers
 // -----------------------------------------------------------------------------------------
-constexpr int kAttnStages = 4;
+constexpr int kAttnStages = 6;   // 6 x 32 KB K|V stages + 2 Q tiles = 224 KB (dual tail items run two 3-deep streams)
 long long* g_attn_timing = nullptr;   // debug: device buffer for the DSG_*_TIMING builds
 
 // The weight tensor maps come in two flavours: full 128-row granules (plain kernel) and 64-row half granules (cluster
@@ -232,8 +232,10 @@ cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, 
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  p.qpairs = (p.N + 2 * ATT_BM - 1) / (2 * ATT_BM);
-  p.num_items = p.B * p.H * p.qpairs;
+  const int q_tiles = (p.N + ATT_BM - 1) / ATT_BM;
+  p.full_pairs = q_tiles / 2;
+  p.reg_items = p.B * p.H * p.full_pairs;
+  p.num_items = p.reg_items + ((q_tiles & 1) ? (p.B * p.H + 1) / 2 : 0);   // lone last tiles are paired across heads
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
   kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
   return cudaGetLastError();

@@ -37,14 +37,24 @@ struct MlpParams {
 
 #ifdef DSG_MLP_TIMING
 #define MLP_T(i) do { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } while (0)
-#define MLP_T_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64()
+#define MLP_T_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64(); \
+  const long long tclk0 = tprev; const long long tns0 = mlp_globaltimer()
+// slots 5 / 6 of the MMA role: SM cycles and nanoseconds of the whole loop (-> the SM clock the kernel really ran at)
+#define MLP_T_CLOCK() do { tacc[5] = clock64() - tclk0; tacc[6] = mlp_globaltimer() - tns0; } while (0)
 #define MLP_T_DUMP(role) do { if (p.timing) for (int _i = 0; _i < 8; ++_i) \
     p.timing[(size_t(blockIdx.x) * 2 + (role)) * 8 + _i] = tacc[_i]; } while (0)
 #else
 #define MLP_T(i) do { } while (0)
 #define MLP_T_DECL do { } while (0)
 #define MLP_T_DUMP(role) do { } while (0)
+#define MLP_T_CLOCK() do { } while (0)
 #endif
+
+__device__ __forceinline__ long long mlp_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int MLP_D = 384;
 constexpr int MLP_HID = 1536;
@@ -300,6 +310,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         commit(acc2_full);
       }
+      MLP_T_CLOCK();
       MLP_T_DUMP(0);
     }
   } else if (warp < 10) {

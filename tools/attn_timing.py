@@ -44,8 +44,8 @@ def main():
         return
     tm = timing[148 * 16:].view(148, 8).double().cpu().mean(0)
     t = timing[:148 * 16].view(148, 2, 8).double().cpu()
-    qpairs = (N + 255) // 256
-    items = B * H * qpairs
+    q_tiles = (N + 127) // 128
+    items = B * H * (q_tiles // 2) + ((B * H + 1) // 2 if q_tiles & 1 else 0)
     tiles_per_wg = items / 148.0 * ((N + 127) // 128)
     print(f"kernel {e0.elapsed_time(e1):.3f} ms; ~{tiles_per_wg:.0f} key tiles per warpgroup per CTA")
     for wg in range(2):

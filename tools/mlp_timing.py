@@ -42,7 +42,12 @@ def main():
     blocks = ((M + 127) // 128) / 148.0
     print(f"mlp_fused mc={mc} {ms:.3f} ms, {4.0 * M * 384 * 1536 / ms / 1e9:.0f} TFLOP/s, {ms * 1e-3 * 1.965e9 / blocks:.0f} clk per row block")
     if have:
-        t = timing.view(148, 2, 8).double().cpu().mean(0)
+        raw = timing.view(148, 2, 8).double().cpu()
+        lead = raw[raw[:, 0, 6] > 0]            # CTAs that issued MMAs (every CTA, or the pair leaders)
+        print(f"  SM clock inside the kernel: {(lead[:, 0, 5] / lead[:, 0, 6]).mean().item() * 1e3:.0f} MHz "
+              f"(cycles / globaltimer ns of the MMA issuer's loop)")
+        raw[:, 0, 5:7] = 0
+        t = raw.mean(0)
         for role, names in ((0, MMA), (1, EPI)):
             print("  " + ["mma", "gelu warp 2"][role] + ": " +
                   ", ".join(f"{n}={t[role][i].item() / blocks:.0f}" for i, n in enumerate(names) if n != "-"))
