@@ -413,7 +413,7 @@ WsLayout ws_layout(const dinoseg* h, int batch) {
   L.qkv = off; off = align_up(off + M * 3 * D * 2, 1024);
   size_t hid_bytes = M * size_t(h->cfg.mlp_hidden) * 2;
   const size_t h1_bytes = M * size_t(h->cfg.head_h1) * 4;
-  const size_t im2col_bytes = size_t(batch) * h->P * IM2COL_K3 * 2;
+  const size_t im2col_bytes = size_t(batch) * h->P * IM2COL_KA * 2;
   if (h1_bytes > hid_bytes) hid_bytes = h1_bytes;
   if (im2col_bytes > hid_bytes) hid_bytes = im2col_bytes;
   L.hid = off; off = align_up(off + hid_bytes, 1024);
@@ -437,7 +437,7 @@ int bind_workspace(dinoseg* h, WorkBufs& w, void* ws, size_t ws_bytes, int batch
   const uint64_t D = h->cfg.embed_dim;
   const uint64_t HID = h->cfg.mlp_hidden, H1 = h->cfg.head_h1;
   bool ok = true;
-  ok &= make_tmap_gemm_a(&w.tm_im2col, w.hid, h->P, batch, IM2COL_K3);   // per frame: tiles never straddle frames
+  ok &= make_tmap_gemm_a(&w.tm_im2col, w.hid, h->P, batch, IM2COL_KA);   // per frame: tiles never straddle frames
   ok &= make_tmap_gemm_a(&w.tm_abuf, w.abuf, M, 1, D);
   ok &= make_tmap_gemm_a(&w.tm_hid, w.hid, M, 1, HID);
   ok &= make_tmap_qkv(&w.tm_qkv3d, w.qkv, batch, h->Ntok, 3 * D);
@@ -448,9 +448,9 @@ int bind_workspace(dinoseg* h, WorkBufs& w, void* ws, size_t ws_bytes, int batch
   ok &= make_tmap_gemm_out(&w.tm_hid_out, w.hid, false, HID, M, 1, HID);
   // head: final-norm tokens as bf16x3 [M, 3D] in the qkv buffer, relu(layer_1) as bf16x3 [M, 3*256] in
   // the hidden buffer, relu(layer_2) fp32 [M, H2] in the (then dead) residual-stream buffer
-  ok &= make_tmap_gemm_a(&w.tm_qkv_a, w.qkv, M, 1, 3 * D);
-  ok &= make_tmap_gemm_out(&w.tm_h1s_out, w.hid, false, 3 * kHeadPart, M, 1, 3 * kHeadPart);
-  ok &= make_tmap_gemm_a(&w.tm_h1s_a, w.hid, M, 1, 3 * kHeadPart);
+  ok &= make_tmap_gemm_a(&w.tm_qkv_a, w.qkv, M, 1, 2 * D);                 // final LN as [hi | lo]
+  ok &= make_tmap_gemm_out(&w.tm_h1s_out, w.hid, false, 2 * kHeadPart, M, 1, 2 * kHeadPart);
+  ok &= make_tmap_gemm_a(&w.tm_h1s_a, w.hid, M, 1, 2 * kHeadPart);
   ok &= make_tmap_gemm_out(&w.tm_h2_out, w.x, true, h->cfg.head_h2, M, 1, h->cfg.head_h2);
   ok &= make_tmap_gemm_out(&w.tm_lin_out, w.x, true, h->cfg.n_classes, M, 1, kLinPitch);   // 'linear' head logits
   (void)H1;
@@ -781,6 +781,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
   }
   {
     GemmParams p = gp(D, IM2COL_K3, h->pe_b);
+    p.a_wrap = IM2COL_KA;
     p.rows_per_batch = h->P; p.batches = batch; p.row_off = 1;   // out row = b*Ntok + 1 + t, + pos[1 + t]
     LaunchScope ls(h, K_GEMM_PATCH, s);
     DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, w.tm_im2col, h->tm_pe, w.tm_x_patch, w.tm_pos_add, p, sms, s)); ++n;
@@ -844,6 +845,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     // 'linear' head (pl_torch_modules.py:127-138): one bf16x3 GEMM -> logits [M, C] (row pitch kLinPitch) -> log_softmax
     {
       GemmParams p = gp(h->cfg.n_classes, 3 * D, h->h1_b);
+      p.a_wrap = 2 * D;
       LaunchScope ls(h, K_GEMM_HEAD, s);
       DSG_CUDA(h, launch_gemm(EPI_BIAS_F32, w.tm_qkv_a, h->tm_h1, w.tm_lin_out, w.tm_lin_out, p, sms, s)); ++n;
     }
@@ -856,11 +858,13 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     {
       GemmParams p = gp(h->cfg.head_h1, 3 * D, h->h1_b);
       p.split_part = kHeadPart;
+      p.a_wrap = 2 * D;
       LaunchScope ls(h, K_GEMM_HEAD, s);
       DSG_CUDA(h, launch_gemm(EPI_RELU_SPLIT_BF16, w.tm_qkv_a, h->tm_h1, w.tm_h1s_out, w.tm_h1s_out, p, sms, s)); ++n;
     }
     {
       GemmParams p = gp(h->cfg.head_h2, 3 * kHeadPart, h->b2);
+      p.a_wrap = 2 * kHeadPart;
       LaunchScope ls(h, K_GEMM_HEAD, s);
       DSG_CUDA(h, launch_gemm(EPI_RELU_F32, w.tm_h1s_a, h->tm_h2, w.tm_h2_out, w.tm_h2_out, p, sms, s)); ++n;
     }

@@ -34,7 +34,7 @@ enum : int {
   EPI_RESID_F32 = 2,  // out f32 = addend + acc + bias      (addend = out: in-place residual add)
   EPI_PATCH_F32 = 3,  // out f32[b, 1 + t] = acc + bias + pos[1 + t]   (addend = positional table)
   EPI_RELU_F32 = 4,   // out f32 = relu(acc + bias)
-  EPI_RELU_SPLIT_BF16 = 5,  // v = relu(acc + bias); out bf16 [rows, 3*split_part] = [hi(v) | lo(v) | hi(v)] (bf16x3 operand)
+  EPI_RELU_SPLIT_BF16 = 5,  // v = relu(acc + bias); out bf16 [rows, 2*split_part] = [hi(v) | lo(v)] (bf16x3 operand)
   EPI_BIAS_F32 = 6,   // out f32 = acc + bias
 };
 
@@ -47,7 +47,8 @@ struct GemmParams {
   const float* bias;    // [N] (may be null)
   float col_scale;
   int scale_cols;
-  int split_part;       // EPI_RELU_SPLIT_BF16: width of each of the three output parts (multiple of 64)
+  int split_part;       // EPI_RELU_SPLIT_BF16: width of each of the two output parts (multiple of 64)
+  int a_wrap;           // > 0: A has only a_wrap columns and the k index wraps (bf16x3 operand stored as [hi | lo])
   long long* timing;    // debug (DSG_GEMM_TIMING builds): [grid][3 roles][8] cycle totals
 };
 
@@ -220,7 +221,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           GEMM_T(1);
           mbar_expect_tx(&full_bar[s], RING_BYTES);
           uint8_t* sr = ring + size_t(s) * RING_BYTES;
-          if constexpr (!RES_A) tma_load_3d(sr, &tmA, &full_bar[s], kb * GEMM_BK, r0, bt);
+          if constexpr (!RES_A) {
+            const int ak = kb * GEMM_BK;
+            tma_load_3d(sr, &tmA, &full_bar[s], (p.a_wrap > 0 && ak >= p.a_wrap) ? ak - p.a_wrap : ak, r0, bt);
+          }
           tma_load_2d(sr + (RES_A ? 0 : GEMM_A_BYTES), &tmW, &full_bar[s], kb * GEMM_BK, nt * GEMM_BN);
           GEMM_T(2);
         }
@@ -412,7 +416,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (col0 < p.split_part) {
               tma_store_3d(&tmOut, sb, col0, p.row_off + r0, bt);
               tma_store_3d(&tmOut, sb + GEMM_STG_BYTES, p.split_part + col0, p.row_off + r0, bt);
-              tma_store_3d(&tmOut, sb, 2 * p.split_part + col0, p.row_off + r0, bt);
             }
           } else {
             if (col0 < p.N) tma_store_3d(&tmOut, sb, col0, p.row_off + r0, bt);

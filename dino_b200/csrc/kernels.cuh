@@ -18,7 +18,9 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 // error; writing x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) and using
 //     x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // brings it to ~2^-16 while staying on the bf16 tensor cores: the three products are obtained from ONE
-// GEMM of three-fold K by laying the operands out as A' = [hi | lo | hi], W' = [hi | hi | lo].  Used for the
+// GEMM of three-fold K over the operands A' = [hi | lo | hi], W' = [hi | hi | lo].  A' is stored as [hi | lo] only:
+// the GEMM producer wraps its A column at 2*K (GemmParams::a_wrap), so the third segment re-reads hi (from L2).
+//  Used for the
 // segmentation head (0.7 % of the FLOPs), whose bf16 rounding otherwise dominates the log-prob error.
 // W [N, K] fp32 -> W' [N, 3*Kp] bf16 (each part zero padded from K to Kp columns)
 __global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int Kp) {
@@ -89,12 +91,13 @@ __global__ void posembed_bicubic_kernel(const float* __restrict__ pos_src /*[G0*
 // ---------------------------------------------------------------------------------------
 // im2col for the 8x8/stride-8 patch-embed conv (reference vision_transformer.py:153,157):
 //   A[b*P + i*g + j][c*64 + ky*8 + kx] = frame[b][c][i*8+ky][j*8+kx]
-// written as a bf16x3 operand [hi | lo | hi] (3 x 192 columns, see split_weight_kernel): the rounding of
+// written as the bf16x3 operand [hi | lo] (2 x 192 columns, see split_weight_kernel): the rounding of
 // the pixels / conv weights to plain bf16 is the largest single contribution to the final log-prob error.
-// One thread moves two image rows of one patch (2 x 32 B in, 3 x 32 B out).
+// One thread moves two image rows of one patch (2 x 32 B in, 2 x 32 B out).
 // ---------------------------------------------------------------------------------------
 constexpr int IM2COL_K = 192;
-constexpr int IM2COL_K3 = 3 * IM2COL_K;
+constexpr int IM2COL_K3 = 3 * IM2COL_K;   // reduction length of the patch-embed GEMM
+constexpr int IM2COL_KA = 2 * IM2COL_K;   // stored columns of its A operand [hi | lo]
 
 __device__ __forceinline__ void split_pack8(const float4& a0, const float4& a1, uint4& hi, uint4& lo) {
   hi.x = pack_bf16x2(a0.x, a0.y); hi.y = pack_bf16x2(a0.z, a0.w);
@@ -124,13 +127,11 @@ __global__ void im2col_patch8_kernel(const float* __restrict__ frames, __nv_bflo
   uint4 h0, l0, h1, l1;
   split_pack8(a0, a1, h0, l0);
   split_pack8(b0, b1, h1, l1);
-  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * IM2COL_K3 + c * 64 + kyp * 16;
+  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * IM2COL_KA + c * 64 + kyp * 16;
   *reinterpret_cast<uint4*>(dst) = h0;
   *reinterpret_cast<uint4*>(dst + 8) = h1;
   *reinterpret_cast<uint4*>(dst + IM2COL_K) = l0;
   *reinterpret_cast<uint4*>(dst + IM2COL_K + 8) = l1;
-  *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K) = h0;
-  *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K + 8) = h1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -202,10 +203,9 @@ __global__ void im2col_u8_kernel(const uint8_t* __restrict__ frames /*[B, H, W, 
   uint4 hi, lo;
   split_pack8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
   const int i = y >> 3, ky = y & 7;
-  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * IM2COL_K3 + c * 64 + ky * 8;
+  __nv_bfloat16* dst = A + (size_t(b) * g * g + size_t(i) * g + j) * IM2COL_KA + c * 64 + ky * 8;
   *reinterpret_cast<uint4*>(dst) = hi;
   *reinterpret_cast<uint4*>(dst + IM2COL_K) = lo;
-  *reinterpret_cast<uint4*>(dst + 2 * IM2COL_K) = hi;
 }
 
 // x[b*Ntok + 0, :] = cls + pos[0]      (reference vision_transformer.py:229-233)
@@ -221,7 +221,7 @@ __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __res
 // LayerNorm (eps inside the sqrt, biased variance; reference :114,:118,:183 with eps=1e-6 :303)
 // fp32 in -> bf16 out (the bf16 copy is the A operand of the following GEMM).  One warp per row.
 // ---------------------------------------------------------------------------------------
-// SPLIT: y is [M, 3*D] = [hi | lo | hi] (bf16x3 operand of the head GEMM, see split_weight_kernel).
+// SPLIT: y is [M, 2*D] = [hi | lo] (bf16x3 operand of the head GEMM, see split_weight_kernel).
 template <int D, bool SPLIT>
 __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -251,7 +251,7 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq * (1.0f / D) + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + size_t(row) * (SPLIT ? 3 * D : D));
+  uint2* yr = reinterpret_cast<uint2*>(y + size_t(row) * (SPLIT ? 2 * D : D));
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
@@ -267,7 +267,6 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
       l.x = pack_bf16x2(a - __uint_as_float(o.x << 16), b - __uint_as_float(o.x & 0xffff0000u));
       l.y = pack_bf16x2(c - __uint_as_float(o.y << 16), d - __uint_as_float(o.y & 0xffff0000u));
       yr[D / 4 + i * 32 + lane] = l;
-      yr[2 * (D / 4) + i * 32 + lane] = o;
     }
   }
 }
