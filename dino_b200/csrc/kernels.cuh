@@ -272,6 +272,34 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
 }
 
 // ---------------------------------------------------------------------------------------
+// Controller-side reduction on the label map (reference docs/index.html "Controller": the
+// potential-field controller steers away from the image half with the most obstacle patches).  Per frame, the number
+// of OUTPUT-MAP pixels of every class left (x < W/2) and right (x >= W/2) of the centre line, W = g*p, computed from
+// the low-res map (patch (i, j) covers p rows and the columns [j*p, (j+1)*p)): counts[b][side][c], int32.
+// One CTA per frame; integer work, exact.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+half_counts_kernel(const uint8_t* __restrict__ lowres, int32_t* __restrict__ counts, int g, int p, int C) {
+  __shared__ int hist[2 * 256];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int b = blockIdx.x;
+  const int half = (g * p) / 2;
+  const uint8_t* low = lowres + size_t(b) * g * g;
+  for (int idx = threadIdx.x; idx < g * g; idx += blockDim.x) {
+    const int j = idx % g;
+    const int c = low[idx];
+    if (c >= C) continue;
+    int left = half - j * p;
+    left = left < 0 ? 0 : (left > p ? p : left);
+    if (left) atomicAdd(&hist[c], left * p);
+    if (p - left) atomicAdd(&hist[C + c], (p - left) * p);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) counts[size_t(b) * 2 * C + i] = hist[i];
+}
+
+// ---------------------------------------------------------------------------------------
 // argmax with torch semantics: first maximum wins, NaN counts as the maximum
 // (reference pl_torch_modules.py:295 torch.argmax)
 // ---------------------------------------------------------------------------------------

@@ -349,6 +349,28 @@ class DINOSeg(nn.Module):
         return lp, low, lab
 
     @torch.no_grad()
+    def half_counts(self, x):
+        """Left / right class pixel counts of the label map, the input of the reference's potential-field controller
+        (docs/index.html "Controller"), without shipping the 480x480 int64 maps to the host.
+
+        x: device frames fp32 [B,3,r,r] (runs the forward) or a device uint8 low-res map [B,g,g] (e.g. from infer()).
+        Returns a device int32 tensor [B, 2, n_classes]: pixels of each class with x < W/2 (index 0) and x >= W/2
+        (index 1) of the (g*p) x (g*p) output map predict() would return."""
+        lib = self._ensure_handle()
+        if x.dtype == torch.uint8 and x.dim() == 3:
+            low = x.contiguous()
+        else:
+            _, low, _ = self.infer(x, want_logprobs=False, want_lowres=True)
+        b, g = int(low.shape[0]), int(low.shape[1])
+        p = 480 // g
+        if p == 0:
+            raise ValueError("resolutions above 3840 have an empty label map (480 // g == 0)")
+        counts = torch.empty((b, 2, self.n_classes), dtype=torch.int32, device=low.device)
+        rc = lib.dinoseg_half_counts(low.data_ptr(), b, g, p, self.n_classes, counts.data_ptr(), self._stream())
+        self._check(rc, "dinoseg_half_counts")
+        return counts
+
+    @torch.no_grad()
     def cls_attention(self, x):
         """Attention of the CLS query in the last kept block: [B, H, N] fp32 (see _Backbone.get_last_selfattention)."""
         lib = self._ensure_handle()

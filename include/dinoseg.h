@@ -103,6 +103,12 @@ int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 int dinoseg_cls_attention(dinoseg_t* h, const float* frames, int batch, float* attn, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Controller-side reduction on the label map (the step after predict() in the robot pipeline, reference
+ * docs/index.html "Controller": left / right obstacle masks for the potential-field controller).
+ * lowres: device uint8 [batch, g, g] as written by dinoseg_forward; the output map is (g*p) x (g*p).
+ * counts: device int32 [batch, 2, n_classes] = pixels of each class with x < g*p/2 (side 0) and x >= g*p/2 (side 1). */
+int dinoseg_half_counts(const uint8_t* lowres, int batch, int g, int p, int n_classes, int32_t* counts, void* stream);
+
 /* Output side of predict() on given log-probs: argmax (first max wins, NaN counts as max)
  * then p x p block replication.  Bit-exact w.r.t. torch.argmax + np.kron.
  * (pl_torch_modules.py:295-298).  rows = batch*g*g. */
@@ -147,7 +153,8 @@ int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const floa
 /* the same kernel run by CTA pairs (tcgen05 cta_group::2, M = 256 per MMA, weights split between the two SMs) when pair != 0 */
 int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                       const float* b2, int M, int pair, void* stream);
-/* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel; 2: fused MLP kernel run by CTA pairs (cta_group::2) */
+/* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel, one CTA per row block; 2: fused MLP kernel run by CTA pairs
+ * (cta_group::2) - the default where the fused kernel applies (embed_dim 384, mlp_hidden 1536) */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
                          float eps, void* stream);

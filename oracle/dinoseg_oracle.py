@@ -211,6 +211,18 @@ def labels_from_logprobs(logprobs: torch.Tensor, batch: int, g: int):
     return low, high
 
 
+def half_counts(labels: np.ndarray, n_classes: int) -> np.ndarray:
+    """Controller-side reduction (reference docs/index.html "Controller"): pixels of every
+    class in the left (x < W/2) and right half of each label map.  labels: int [B, H, W] -> int64 [B, 2, n_classes]."""
+    labels = np.asarray(labels)
+    b, _, w = labels.shape
+    out = np.zeros((b, 2, n_classes), dtype=np.int64)
+    for i in range(b):
+        out[i, 0] = np.bincount(labels[i, :, : w // 2].ravel(), minlength=n_classes)[:n_classes]
+        out[i, 1] = np.bincount(labels[i, :, w // 2:].ravel(), minlength=n_classes)[:n_classes]
+    return out
+
+
 def argmax_replicate_numpy(logprobs: np.ndarray, batch: int, g: int):
     """Independent restatement of the tail in index form: out[b,y,x] = low[b, y//p, x//p];
     argmax = first maximum, NaN counts as maximum (torch.argmax semantics)."""

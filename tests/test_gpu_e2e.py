@@ -294,6 +294,22 @@ def test_cls_attention_against_reference(name):
     assert err <= tol * float(ref.max()), (err, float(ref.max()))
 
 
+@pytest.mark.parametrize("res", [240, 24, 40])
+def test_half_counts_match_oracle(res):
+    """Controller-side reduction: left / right class pixel counts computed on the GPU from
+    the low-res map equal a bincount over the halves of the int64 label map predict() returns (bit-exact; res 24 and
+    40 have an odd patch grid, where the centre line cuts through a column of patches)."""
+    m, cfg, sd = _model("vit_small", 1, 7, "trained_like")
+    x = synthetic.make_frames(3, res, seed=9).cuda()
+    _, low, lab = m.infer(x, want_logprobs=False, want_lowres=True, want_labels=True)
+    got = m.half_counts(x).cpu().numpy()
+    again = m.half_counts(low).cpu().numpy()
+    ref = O.half_counts(lab.cpu().numpy(), cfg["n_classes"])
+    assert got.dtype == np.int32 and got.shape == (3, 2, cfg["n_classes"])
+    assert np.array_equal(got, ref) and np.array_equal(again, ref)
+    assert int(got.sum()) == 3 * lab.shape[1] * lab.shape[2]
+
+
 def test_fused_mlp_matches_unfused_path():
     """ViT-S runs fc1 -> GELU -> fc2 in one fused kernel; the unfused LN / fc1 / fc2 GEMM path (what ViT-B uses)
     must give the same log-probs up to bf16 rounding noise, and both must match the oracle."""

@@ -123,3 +123,16 @@ def test_oracle_cls_attention_matches_reference(name):
     got = O.last_selfattention_cls(sd, cfg, x).numpy()
     assert got.shape == gd["cls_attn"].shape
     assert np.abs(got - gd["cls_attn"]).max() <= 1e-6
+
+
+def test_half_counts_oracle():
+    """Left / right class counts: brute force over pixels on a small odd-width map."""
+    rng = np.random.default_rng(0)
+    lab = rng.integers(0, 5, size=(2, 6, 9))
+    got = O.half_counts(lab, 5)
+    for b in range(2):
+        for side in range(2):
+            for c in range(5):
+                n = sum(1 for y in range(6) for x in range(9) if lab[b, y, x] == c and (x >= 4) == bool(side))
+                assert got[b, side, c] == n
+    assert got.sum() == lab.size
