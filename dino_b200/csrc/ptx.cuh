@@ -84,6 +84,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");                                          // of spinning on the issue slots of the SMSP
   return ok != 0;
 }
+// non-blocking test of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait, fully inline (a real call here would force ptxas to spill every live register of the
 // softmax warps around it): fast path = one try_wait; slow path spins with a clock64() deadline and
 // traps, so a protocol bug ends in cudaErrorLaunchFailure instead of a hung GPU.
