@@ -189,6 +189,53 @@ cudaError_t launch_gemm_tt(const CUtensorMap& a, const CUtensorMap& w, const CUt
   return cudaGetLastError();
 }
 
+// CTA-pair launch (cta_group::2, gemm.cuh): `w` must be a tensor map with 96-row boxes (half a W tile).
+// RES_A: the A row block (K <= 384) stays in shared memory for all n-tiles of its row-block pair.
+template <int EPI, bool RES_A>
+cudaError_t launch_gemm_pair_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
+                               const GemmParams& p, int num_sms, cudaStream_t s) {
+  auto kern = gemm_bf16_tn_kernel<EPI, RES_A, true>;
+  constexpr size_t smem = gemm_smem_bytes(EPI, RES_A, true);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
+  const int m_tiles = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM * p.batches;
+  const long long units = RES_A ? (m_tiles + 1) / 2 : (long long)n_tiles * ((m_tiles + 1) / 2);
+  if (units <= 0 || units > INT32_MAX || p.K % GEMM_BK != 0 || n_tiles * GEMM_BN > GEMM_MAX_N) return cudaErrorInvalidValue;
+  const int max_pairs = num_sms / 2;
+  GemmParams pp = p;
+  pp.timing = g_attn_timing;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * unsigned(units < max_pairs ? units : max_pairs));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a, w, out, add, pp);
+}
+
+template <int EPI>
+cudaError_t launch_gemm_pair(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
+                             const GemmParams& p, int num_sms, cudaStream_t s) {
+  // resident A (K <= 384: ViT-S qkv) measured best inside the whole step (7.56-7.71 k frames/s against 7.51-7.58 k
+  // for streaming pairs and 7.47-7.54 k for single-CTA tiles); DINOSEG_GEMM_PAIR_RESA=0 selects the streaming pairs
+  static const bool res_env = [] { const char* e = getenv("DINOSEG_GEMM_PAIR_RESA"); return e ? atoi(e) != 0 : true; }();
+  const bool res_a = res_env && p.K <= GEMM_RES_KB * GEMM_BK && p.N > GEMM_BN && p.a_wrap == 0;
+  return res_a ? launch_gemm_pair_t<EPI, true>(a, w, out, add, p, num_sms, s)
+               : launch_gemm_pair_t<EPI, false>(a, w, out, add, p, num_sms, s);
+}
+
 // The resident-A variant (K <= 384, several n-tiles) halves the L2 -> SM traffic per tile, but on B200 it
 // measured SLOWER than the streaming variant (qkv 0.235 vs 0.200 ms, fc1 0.366 vs 0.339 ms): the single
 // A buffer cannot be refilled early enough for the next row block (gemm.cuh).  It is kept selectable
@@ -297,6 +344,7 @@ struct BlockW {
   CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
   CUtensorMap tm_fc1_g, tm_fc2_g;   // 128-row granule views for the fused MLP kernel
   CUtensorMap tm_fc1_h, tm_fc2_h;   // 64-row half granules (CTA-pair variant)
+  CUtensorMap tm_qkv_h;             // 96-row half W tiles (CTA-pair GEMM)
 };
 
 struct WeightSlot {
@@ -367,6 +415,7 @@ struct dinoseg {
   int debug_stop = 0;
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
+  bool gemm_pair = true;            // qkv GEMM as CTA pairs (cta_group::2)
   bool mlp_pair = false;       // ... as CTA pairs (cta_group::2), half the weights per SM
 
   // optional per-kernel-kind timing (cudaEvents around every launch of a forward)
@@ -525,6 +574,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->device = device;
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
   h->mlp_pair = h->fused_mlp;       // CTA pairs measured 1.6 % faster than single CTAs (0.486 vs 0.494 ms per launch)
+  if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
     const int m = atoi(mode);
     h->fused_mlp = h->fused_mlp && m != 0;
@@ -580,6 +630,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     add_slot(h, pre + "mlp.fc2.weight", 1, b.fc2_w, {D, HID}); add_slot(h, pre + "mlp.fc2.bias", 0, b.fc2_b, {D});
     bool ok = true;
     ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, GEMM_BN);
+    ok &= make_tmap_2d(&b.tm_qkv_h, b.qkv_w, 3 * D, D, D, GEMM_BN / 2);
     ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc1, b.fc1_w, HID, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, GEMM_BN);
@@ -797,7 +848,13 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       GemmParams p = gp(3 * D, D, b.qkv_b);
       p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
       LaunchScope ls(h, K_GEMM_QKV, s);
-      DSG_CUDA(h, launch_gemm(EPI_BF16, w.tm_abuf, b.tm_qkv, w.tm_qkv_out, w.tm_qkv_out, p, sms, s)); ++n;
+      if (h->gemm_pair &&
+          launch_gemm_pair<EPI_BF16>(w.tm_abuf, b.tm_qkv_h, w.tm_qkv_out, w.tm_qkv_out, p, sms, s) != cudaSuccess) {
+        (void)cudaGetLastError();   // no 2-CTA clusters on this device / partition: one CTA per tile
+        h->gemm_pair = false;
+      }
+      if (!h->gemm_pair) DSG_CUDA(h, launch_gemm(EPI_BF16, w.tm_abuf, b.tm_qkv, w.tm_qkv_out, w.tm_qkv_out, p, sms, s));
+      ++n;
     }
     if (stop == 2 + 3 * i) { h->launches = n; return 0; }
     {
@@ -1101,6 +1158,23 @@ int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, 
   }
   if (!ok) return -2;
   return launch_gemm(epi, ta, tw, to, tadd, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
+                         float col_scale, int scale_cols, void* stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0 || (K % GEMM_BK) != 0 || N % 8 != 0) return -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap ta, tw, to;
+  GemmParams p{};
+  p.N = N; p.K = K; p.bias = bias; p.col_scale = col_scale; p.scale_cols = scale_cols;
+  p.rows_per_batch = M; p.batches = 1;
+  bool ok = make_tmap_2d(&tw, W, N, K, K, GEMM_BN / 2);
+  ok &= make_tmap_gemm_a(&ta, A, M, 1, K);
+  ok &= make_tmap_gemm_out(&to, out, false, N, M, 1, ldo);
+  if (!ok) return -2;
+  return launch_gemm_pair<EPI_BF16>(ta, tw, to, to, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_debug_set_attn_timing(long long* dev_ptr) {

@@ -85,9 +85,16 @@ constexpr int GEMM_MAX_N = 3072;                      // bias vector staged in s
 constexpr int GEMM_BIAS_BYTES = GEMM_MAX_N * 4;
 constexpr int GEMM_RES_KB = 6;                        // resident-A variant: up to 6 k-blocks (K <= 384)
 __host__ __device__ constexpr int gemm_res_wstages(int epi) { return gemm_nbuf(epi) == 4 ? 2 : 3; }
-__host__ __device__ constexpr size_t gemm_smem_bytes(int epi, bool res_a) {
-  return (res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(gemm_res_wstages(epi)) * GEMM_B_BYTES
-                : size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES) +
+// CTA-pair variant (cta_group::2): a stage holds this CTA's A tile and HALF of the W tile (96 rows)
+constexpr int GEMM_PAIR_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES / 2;   // 28 KB
+__host__ __device__ constexpr int gemm_pair_stages(int epi) { return gemm_stages(epi) + 1; }
+// ... or, with the A row block resident (K <= 384), only the half W tile (12 KB)
+constexpr int GEMM_PAIR_RES_WSTAGES = 6;
+__host__ __device__ constexpr size_t gemm_smem_bytes(int epi, bool res_a, bool pair = false) {
+  return (pair ? (res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(GEMM_PAIR_RES_WSTAGES) * (GEMM_B_BYTES / 2)
+                        : size_t(gemm_pair_stages(epi)) * GEMM_PAIR_STAGE_BYTES)
+          : res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(gemm_res_wstages(epi)) * GEMM_B_BYTES
+                  : size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES) +
          size_t(gemm_nbuf(epi)) * GEMM_STG_BYTES + GEMM_BIAS_BYTES + 1024 /*align*/ + 256;
 }
 
@@ -109,7 +116,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x >= 0.f ? fmaf(-x, w, x) : x * w;
 }
 
-template <int EPI, bool RES_A>
+// PAIR = true: the kernel runs as CTA pairs (clusters of two, tcgen05 cta_group::2).  A pair computes a 256 x 192
+// tile: one M = 256 instruction per K step, issued by the leader CTA (cluster rank 0) and executed by both SMs, each
+// on its own 128 rows of A and its own accumulator, with the 192 W rows split 96 / 96 between the two CTAs' shared
+// memories.  The plain kernel is bound by the L2 -> SM delivery of its operands (40 KB per k-block per SM at
+// ~42 B/clk/SM against 512 clk of MMA work); the pair loads 28 KB per k-block per SM.  Barriers as in mlp.cuh: what
+// the issuer waits on lives in the leader CTA and collects both CTAs' arrivals, what it signals is multicast.
+template <int EPI, bool RES_A, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
@@ -118,8 +131,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool HAS_ADD = gemm_has_addend(EPI);
   constexpr bool SPLIT = EPI == EPI_RELU_SPLIT_BF16;
   constexpr int BPC = SPLIT ? 2 : 1;             // staging buffers per chunk
-  constexpr int STAGES = RES_A ? gemm_res_wstages(EPI) : gemm_stages(EPI);   // ring depth (W only if RES_A)
-  constexpr int RING_BYTES = RES_A ? GEMM_B_BYTES : GEMM_STAGE_BYTES;
+  constexpr int STAGES = PAIR ? (RES_A ? GEMM_PAIR_RES_WSTAGES : gemm_pair_stages(EPI))
+                              : (RES_A ? gemm_res_wstages(EPI) : gemm_stages(EPI));
+  constexpr int RING_BYTES = PAIR ? (RES_A ? GEMM_B_BYTES / 2 : GEMM_PAIR_STAGE_BYTES)
+                                  : (RES_A ? GEMM_B_BYTES : GEMM_STAGE_BYTES);
+  constexpr uint32_t NCTA = PAIR ? 2 : 1;
   constexpr int A_RES_BYTES = RES_A ? GEMM_RES_KB * GEMM_A_BYTES : 0;
   constexpr int NBUF = gemm_nbuf(EPI);
   constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 bytes per row)
@@ -152,14 +168,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int m_tiles_pb = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM;
   const int m_total = m_tiles_pb * p.batches;
-  const int total_tiles = n_tiles * m_total;
+  // PAIR: the unit is a pair of neighbouring row blocks; cluster c takes the pair tiles c, c + G/2, ... and rank r the
+  // r-th row block of the pair (a row block past the end loads zeros and stores nothing)
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
+  const int m_units = PAIR ? (m_total + 1) / 2 : m_total;
+  const int total_tiles = n_tiles * m_units;
+  const int unit0 = PAIR ? int(blockIdx.x) / 2 : int(blockIdx.x);
+  const int ustride = PAIR ? int(gridDim.x) / 2 : int(gridDim.x);
   // tiles of this CTA: plain = tile ids bid, bid+G, ... (n fastest); RES_A = every n-tile of row blocks bid, bid+G, ...
-  const int my_tiles = RES_A ? (int(blockIdx.x) < m_total ? ((m_total - 1 - int(blockIdx.x)) / int(gridDim.x) + 1) * n_tiles : 0)
-                             : (int(blockIdx.x) < total_tiles ? (total_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0);
+  const int my_tiles = RES_A ? (unit0 < m_units ? ((m_units - 1 - unit0) / ustride + 1) * n_tiles : 0)
+                             : (unit0 < total_tiles ? (total_tiles - 1 - unit0) / ustride + 1 : 0);
+  auto arrive_leader = [&](uint64_t* bar) {
+    if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar, 0));
+    else mbar_arrive(bar);
+  };
   auto tile_coords = [&](int t, int& mt, int& nt) {
     if constexpr (RES_A) {
-      mt = int(blockIdx.x) + (t / n_tiles) * int(gridDim.x);
+      mt = (unit0 + (t / n_tiles) * ustride) * (PAIR ? 2 : 1) + int(cta_rank);
       nt = t % n_tiles;
+    } else if constexpr (PAIR) {
+      const int tile = unit0 + t * ustride;
+      nt = tile % n_tiles;
+      mt = (tile / n_tiles) * 2 + int(cta_rank);
     } else {
       const int tile = int(blockIdx.x) + t * int(gridDim.x);
       nt = tile % n_tiles;
@@ -182,17 +212,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], GEMM_EPI_THREADS / 32);
+      mbar_init(&acc_empty[s], GEMM_EPI_THREADS / 32 * NCTA);
     }
     for (int s = 0; s < NBUF; ++s) mbar_init(&add_bar[s], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   // bias (zero padded to a multiple of the tile width) once per persistent CTA
   for (int i = threadIdx.x; i < n_tiles * GEMM_BN; i += GEMM_THREADS)
     sbias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -211,29 +245,54 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (RES_A) {
             if (nt == 0) {                         // (re)fill the resident A block, k-block by k-block
               mbar_wait(&a_empty[kb], (mi & 1) ^ 1);
-              mbar_expect_tx(&a_full[kb], GEMM_A_BYTES);
-              tma_load_3d(smem + size_t(kb) * GEMM_A_BYTES, &tmA, &a_full[kb], kb * GEMM_BK, r0, bt);
+              if constexpr (PAIR) {
+                if (cta_rank == 0) mbar_expect_tx(&a_full[kb], 2 * GEMM_A_BYTES);
+                tma_load_3d_pair(smem + size_t(kb) * GEMM_A_BYTES, &tmA, mapa_rank(&a_full[kb], 0), kb * GEMM_BK, r0, bt);
+              } else {
+                mbar_expect_tx(&a_full[kb], GEMM_A_BYTES);
+                tma_load_3d(smem + size_t(kb) * GEMM_A_BYTES, &tmA, &a_full[kb], kb * GEMM_BK, r0, bt);
+              }
             }
           }
           const int s = kc % STAGES;
           GEMM_T(0);
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
           GEMM_T(1);
-          mbar_expect_tx(&full_bar[s], RING_BYTES);
           uint8_t* sr = ring + size_t(s) * RING_BYTES;
-          if constexpr (!RES_A) {
-            const int ak = kb * GEMM_BK;
-            tma_load_3d(sr, &tmA, &full_bar[s], (p.a_wrap > 0 && ak >= p.a_wrap) ? ak - p.a_wrap : ak, r0, bt);
+          if constexpr (PAIR) {
+            // my A tile and my 96 rows of the W tile; both CTAs' bytes complete on the leader's barrier
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * RING_BYTES);
+            const uint32_t bar = mapa_rank(&full_bar[s], 0);
+            if constexpr (!RES_A) {
+              const int ak = kb * GEMM_BK;
+              tma_load_3d_pair(sr, &tmA, bar, (p.a_wrap > 0 && ak >= p.a_wrap) ? ak - p.a_wrap : ak, r0, bt);
+            }
+            tma_load_2d_pair(sr + (RES_A ? 0 : GEMM_A_BYTES), &tmW, bar, kb * GEMM_BK,
+                             nt * GEMM_BN + int(cta_rank) * (GEMM_BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[s], RING_BYTES);
+            if constexpr (!RES_A) {
+              const int ak = kb * GEMM_BK;
+              tma_load_3d(sr, &tmA, &full_bar[s], (p.a_wrap > 0 && ak >= p.a_wrap) ? ak - p.a_wrap : ak, r0, bt);
+            }
+            tma_load_2d(sr + (RES_A ? 0 : GEMM_A_BYTES), &tmW, &full_bar[s], kb * GEMM_BK, nt * GEMM_BN);
           }
-          tma_load_2d(sr + (RES_A ? 0 : GEMM_A_BYTES), &tmW, &full_bar[s], kb * GEMM_BK, nt * GEMM_BN);
           GEMM_T(2);
         }
       }
       GEMM_T_DUMP(0);
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN, 0);
+    if (cta_rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BM : GEMM_BM, GEMM_BN, 0);
+      auto wait = [&](uint64_t* bar, uint32_t parity) {
+        if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) tc_commit_pair(bar, uint16_t(3));
+        else tc_commit(bar);
+      };
       uint32_t kc = 0;
       GEMM_T_DECL;
       for (int ti = 0; ti < my_tiles; ++ti) {
@@ -241,7 +300,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tile_coords(ti, mt, nt);
         const int as = ti & 1;
         GEMM_T(7);
-        mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+        wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);        // epilogue has drained this accumulator stage
         GEMM_T(0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as) * ACC_STRIDE;
@@ -249,10 +308,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
           const int s = kc % STAGES;
           if constexpr (RES_A) {
-            if (nt == 0) mbar_wait(&a_full[kb], mi & 1);
+            if (nt == 0) wait(&a_full[kb], mi & 1);
           }
           GEMM_T(7);
-          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+          wait(&full_bar[s], (kc / STAGES) & 1);
           GEMM_T(1);
           tc_fence_after();
           const uint32_t sr = smem_u32(ring + size_t(s) * RING_BYTES);
@@ -261,15 +320,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >>4 -> +2)
-            umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_ss_pair(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            else umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[s]);
+          commit(&empty_bar[s]);
           if constexpr (RES_A) {
-            if (nt == n_tiles - 1) tc_commit(&a_empty[kb]);   // the next row block may overwrite this k-block
+            if (nt == n_tiles - 1) commit(&a_empty[kb]);      // the next row block may overwrite this k-block
           }
           GEMM_T(2);
         }
-        tc_commit(&acc_full[as]);
+        commit(&acc_full[as]);
       }
       GEMM_T_DUMP(1);
     }
@@ -343,7 +403,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (c == NCH - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);   // the MMA warp may start tile ti+2 in this stage
+          if (lane == 0) arrive_leader(&acc_empty[as]); // the MMA warp may start tile ti+2 in this stage
         }
 #pragma unroll
         for (int i = 0; i < HC; i += 4) {
@@ -430,7 +490,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (PAIR) cluster_sync_all();          // both CTAs are done with each other's barriers and TMEM
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace dsg
