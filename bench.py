@@ -332,7 +332,7 @@ def main():
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
                     # exact workload (profiles/r01_attn_ncu_full.csv): 531.1 MB + 158.0 MB; algorithmic = 531 MB of
                     # q/k/v read once + 177 MB of output
-                    "traffic": 689.2e6 if (B, res, args.arch) == (64, 480, "vit_small") else None,
+                    "traffic": 690.5e6 if (B, res, args.arch) == (64, 480, "vit_small") else None,
                     "traffic_unit": "bytes per launch (ncu, profiles/r01_attn_ncu_full.csv)",
                     "peak_source": peaks_src + ", sustained figure (kernel timed inside a long step)",
                     "flops_per_launch": f_launch, "launches_timed": att_n, "avg_launch_ms": att_ms / att_n,

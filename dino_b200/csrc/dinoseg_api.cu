@@ -281,8 +281,8 @@ cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, 
   }
   const int q_tiles = (p.N + ATT_BM - 1) / ATT_BM;
   p.full_pairs = q_tiles / 2;
-  p.reg_items = p.B * p.H * p.full_pairs;
-  p.num_items = p.reg_items + ((q_tiles & 1) ? (p.B * p.H + 1) / 2 : 0);   // lone last tiles are paired across heads
+  p.lone = q_tiles & 1;
+  p.num_items = p.B * p.H * p.full_pairs + (p.lone ? (p.B * p.H + 1) / 2 : 0);   // lone last tiles are paired across heads
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
   kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
   return cudaGetLastError();
