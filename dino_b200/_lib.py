@@ -60,7 +60,7 @@ SIGNATURES = {
     "dinoseg_op_mlp_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p]),
     "dinoseg_op_gemm_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                       C.c_float, C.c_int, C.c_void_p]),
+                                       C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "dinoseg_half_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dinoseg_set_fused_mlp": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

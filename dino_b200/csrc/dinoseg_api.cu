@@ -344,7 +344,7 @@ struct BlockW {
   CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
   CUtensorMap tm_fc1_g, tm_fc2_g;   // 128-row granule views for the fused MLP kernel
   CUtensorMap tm_fc1_h, tm_fc2_h;   // 64-row half granules (CTA-pair variant)
-  CUtensorMap tm_qkv_h;             // 96-row half W tiles (CTA-pair GEMM)
+  CUtensorMap tm_qkv_h, tm_fc1_p, tm_fc2_p;   // 96-row half W tiles (CTA-pair GEMMs)
 };
 
 struct WeightSlot {
@@ -631,6 +631,8 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     bool ok = true;
     ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_qkv_h, b.qkv_w, 3 * D, D, D, GEMM_BN / 2);
+    ok &= make_tmap_2d(&b.tm_fc1_p, b.fc1_w, HID, D, D, GEMM_BN / 2);
+    ok &= make_tmap_2d(&b.tm_fc2_p, b.fc2_w, D, HID, HID, GEMM_BN / 2);
     ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc1, b.fc1_w, HID, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_fc2, b.fc2_w, D, HID, HID, GEMM_BN);
@@ -886,12 +888,24 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       {
         GemmParams p = gp(HID, D, b.fc1_b);
         LaunchScope ls(h, K_GEMM_FC1, s);
-        DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, w.tm_abuf, b.tm_fc1, w.tm_hid_out, w.tm_hid_out, p, sms, s)); ++n;
+        if (h->gemm_pair &&
+            launch_gemm_pair<EPI_GELU_BF16>(w.tm_abuf, b.tm_fc1_p, w.tm_hid_out, w.tm_hid_out, p, sms, s) != cudaSuccess) {
+          (void)cudaGetLastError();
+          h->gemm_pair = false;
+        }
+        if (!h->gemm_pair) DSG_CUDA(h, launch_gemm(EPI_GELU_BF16, w.tm_abuf, b.tm_fc1, w.tm_hid_out, w.tm_hid_out, p, sms, s));
+        ++n;
       }
       {
         GemmParams p = gp(D, HID, b.fc2_b);
         LaunchScope ls(h, K_GEMM_FC2, s);
-        DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_hid, b.tm_fc2, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
+        if (h->gemm_pair &&
+            launch_gemm_pair<EPI_RESID_F32>(w.tm_hid, b.tm_fc2_p, w.tm_x_out, w.tm_x_out, p, sms, s) != cudaSuccess) {
+          (void)cudaGetLastError();
+          h->gemm_pair = false;
+        }
+        if (!h->gemm_pair) DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_hid, b.tm_fc2, w.tm_x_out, w.tm_x_out, p, sms, s));
+        ++n;
       }
     }
     if (stop == 4 + 3 * i) { h->launches = n; return 0; }
@@ -1160,9 +1174,11 @@ int dinoseg_op_gemm(const void* A, const void* W, const float* bias, void* out, 
   return launch_gemm(epi, ta, tw, to, tadd, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
-int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
+int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo, int epi,
                          float col_scale, int scale_cols, void* stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0 || (K % GEMM_BK) != 0 || N % 8 != 0) return -1;
+  if (epi != EPI_BF16 && epi != EPI_GELU_BF16 && epi != EPI_RESID_F32) return -1;
+  const bool f32 = gemm_out_is_f32(epi);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1172,9 +1188,13 @@ int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* 
   p.rows_per_batch = M; p.batches = 1;
   bool ok = make_tmap_2d(&tw, W, N, K, K, GEMM_BN / 2);
   ok &= make_tmap_gemm_a(&ta, A, M, 1, K);
-  ok &= make_tmap_gemm_out(&to, out, false, N, M, 1, ldo);
+  ok &= make_tmap_gemm_out(&to, out, f32, N, M, 1, ldo);
   if (!ok) return -2;
-  return launch_gemm_pair<EPI_BF16>(ta, tw, to, to, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = epi == EPI_BF16        ? launch_gemm_pair<EPI_BF16>(ta, tw, to, to, p, sms, s)
+                        : epi == EPI_GELU_BF16 ? launch_gemm_pair<EPI_GELU_BF16>(ta, tw, to, to, p, sms, s)
+                                               : launch_gemm_pair<EPI_RESID_F32>(ta, tw, to, to, p, sms, s);
+  return e == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_debug_set_attn_timing(long long* dev_ptr) {

@@ -89,9 +89,9 @@ __host__ __device__ constexpr int gemm_res_wstages(int epi) { return gemm_nbuf(e
 constexpr int GEMM_PAIR_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES / 2;   // 28 KB
 __host__ __device__ constexpr int gemm_pair_stages(int epi) { return gemm_stages(epi) + 1; }
 // ... or, with the A row block resident (K <= 384), only the half W tile (12 KB)
-constexpr int GEMM_PAIR_RES_WSTAGES = 6;
+__host__ __device__ constexpr int gemm_pair_res_wstages(int epi) { return gemm_nbuf(epi) == 4 ? 3 : 6; }
 __host__ __device__ constexpr size_t gemm_smem_bytes(int epi, bool res_a, bool pair = false) {
-  return (pair ? (res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(GEMM_PAIR_RES_WSTAGES) * (GEMM_B_BYTES / 2)
+  return (pair ? (res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(gemm_pair_res_wstages(epi)) * (GEMM_B_BYTES / 2)
                         : size_t(gemm_pair_stages(epi)) * GEMM_PAIR_STAGE_BYTES)
           : res_a ? size_t(GEMM_RES_KB) * GEMM_A_BYTES + size_t(gemm_res_wstages(epi)) * GEMM_B_BYTES
                   : size_t(gemm_stages(epi)) * GEMM_STAGE_BYTES) +
@@ -131,7 +131,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool HAS_ADD = gemm_has_addend(EPI);
   constexpr bool SPLIT = EPI == EPI_RELU_SPLIT_BF16;
   constexpr int BPC = SPLIT ? 2 : 1;             // staging buffers per chunk
-  constexpr int STAGES = PAIR ? (RES_A ? GEMM_PAIR_RES_WSTAGES : gemm_pair_stages(EPI))
+  constexpr int STAGES = PAIR ? (RES_A ? gemm_pair_res_wstages(EPI) : gemm_pair_stages(EPI))
                               : (RES_A ? gemm_res_wstages(EPI) : gemm_stages(EPI));
   constexpr int RING_BYTES = PAIR ? (RES_A ? GEMM_B_BYTES / 2 : GEMM_PAIR_STAGE_BYTES)
                                   : (RES_A ? GEMM_B_BYTES : GEMM_STAGE_BYTES);

@@ -141,9 +141,9 @@ int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind,
 int dinoseg_op_gemm(const void* A_bf16, const void* W_bf16, const float* bias, void* out, int M, int N, int K,
                     int ldo, int epi, float col_scale, int scale_cols, const float* pos, int P, int Ntok,
                     void* stream);
-/* dinoseg_op_gemm with the bf16 epilogue (epi 0) run by CTA pairs (tcgen05 cta_group::2: 256 x 192 tiles, the W tile
- * split between the two SMs) - how the qkv GEMM of the forward is launched */
-int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo,
+/* dinoseg_op_gemm (epilogues 0 bf16, 1 GELU bf16, 2 residual fp32) run by CTA pairs (tcgen05 cta_group::2: 256 x 192
+ * tiles, the W tile split between the two SMs) - how the qkv GEMM (and ViT-B's fc1 / fc2) of the forward are launched */
+int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo, int epi,
                          float col_scale, int scale_cols, void* stream);
 /* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16 (q pre-scaled) */
 int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int H, void* stream);

@@ -21,7 +21,7 @@ def main():
                                     C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     M = 64 * 3601
     lib.dinoseg_op_gemm_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                         C.c_float, C.c_int, C.c_void_p]
+                                         C.c_int, C.c_float, C.c_int, C.c_void_p]
     pair = os.environ.get("GEMM_PAIR", "0") == "1"      # qkv through the CTA-pair kernel (leader CTAs carry the MMA role)
     shapes = (("qkv", 1152, 384, 0),) if pair else (("qkv", 1152, 384, 0), ("fc1", 1536, 384, 1), ("proj", 384, 384, 2), ("fc2", 384, 1536, 2))
     for name, N, K, epi in shapes:
@@ -33,7 +33,7 @@ def main():
         assert lib.dinoseg_debug_set_attn_timing(timing.data_ptr()) == 0
         def run():
             if pair:
-                return lib.dinoseg_op_gemm_pair(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, N, 0.125,
+                return lib.dinoseg_op_gemm_pair(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, N, 0, 0.125,
                                                 N // 3, None)
             return lib.dinoseg_op_gemm(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, N, epi, 0.125,
                                        N // 3, None, 0, 0, None)

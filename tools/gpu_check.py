@@ -92,9 +92,9 @@ def check_gemm(name, M, N, K, epi, with_bias=True, P=0, Ntok=0):
                    n_bad=int(bad.shape[0]), first_bad=first_bad)
 
 
-def check_gemm_pair(name, M, N, K):
-    """bf16-epilogue GEMM run by CTA pairs (cta_group::2) vs fp32 torch on the same bf16 operands, and bit-identical
-    to the single-CTA kernel (same MMAs per output row, same epilogue)."""
+def check_gemm_pair(name, M, N, K, epi=0):
+    """GEMM run by CTA pairs (cta_group::2) vs fp32 torch on the same bf16 operands, and bit-identical to the
+    single-CTA kernel (same MMAs per output row, same epilogue).  epi: 0 bf16 (q scaled), 1 GELU bf16, 2 residual fp32."""
     torch, L, lib = _imports()
     torch.manual_seed(1)
     dev = "cuda"
@@ -102,16 +102,24 @@ def check_gemm_pair(name, M, N, K):
     W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
     bias = torch.randn(N, device=dev) * 0.1
     ref = A.float() @ W.float().t() + bias
-    ref[:, :N // 3] *= 0.125
-    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-    one = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-    rc = lib.dinoseg_op_gemm_pair(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, N, 0.125, N // 3, None)
-    rc1 = lib.dinoseg_op_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(one), M, N, K, N, L.EPI_BF16, 0.125, N // 3, None, 0, 0,
-                              None)
+    scale_cols = 0
+    if epi == L.EPI_BF16:
+        scale_cols = N // 3
+        ref[:, :scale_cols] *= 0.125
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    elif epi == L.EPI_GELU_BF16:
+        ref = torch.nn.functional.gelu(ref)
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    else:
+        out = torch.randn(M, N, device=dev)
+        ref = ref + out
+    one = out.clone()
+    rc = lib.dinoseg_op_gemm_pair(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, N, epi, 0.125, scale_cols, None)
+    rc1 = lib.dinoseg_op_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(one), M, N, K, N, epi, 0.125, scale_cols, None, 0, 0, None)
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    tol = 2e-2 * scale
+    tol = (2e-2 if out.dtype == torch.bfloat16 else 2e-3) * scale
     same = bool(torch.equal(out, one))
     bad = ((out.float() - ref).abs() > tol).nonzero()
     return _report(name, rc == 0 and rc1 == 0 and err <= tol and same, rc=rc, max_abs_err=err, ref_absmax=scale, tol=tol,
@@ -269,6 +277,8 @@ def _checks():
         "gemm_pair_qkv": lambda: check_gemm_pair("gemm_pair_qkv", 1000, 1152, 384),
         "gemm_pair_big": lambda: check_gemm_pair("gemm_pair_big", 148 * 128 * 3 + 300, 1152, 384),
         "gemm_pair_vitb": lambda: check_gemm_pair("gemm_pair_vitb", 901 * 3, 2304, 768),
+        "gemm_pair_gelu": lambda: check_gemm_pair("gemm_pair_gelu", 901 * 3, 3072, 768, L.EPI_GELU_BF16),
+        "gemm_pair_resid": lambda: check_gemm_pair("gemm_pair_resid", 901 * 3, 768, 3072, L.EPI_RESID_F32),
         "gemm_gelu": lambda: check_gemm("gemm_gelu", 901, 1536, 384, L.EPI_GELU_BF16),
         "gemm_resid_k1536": lambda: check_gemm("gemm_resid_k1536", 901, 384, 1536, L.EPI_RESID_F32),
         "gemm_patch": lambda: check_gemm("gemm_patch", 2 * 900, 384, 192, L.EPI_PATCH_F32, P=900, Ntok=901),
@@ -292,7 +302,7 @@ def _checks():
 def check_names():
     return [
         "layernorm_384", "layernorm_768", "posembed_30", "posembed_60", "posembed_28", "posembed_vitb_60", "im2col",
-        "argmax_replicate", "argmax_replicate_odd", "gemm_tile", "gemm_k384", "gemm_qkv", "gemm_pair_small", "gemm_pair_qkv", "gemm_pair_big", "gemm_pair_vitb", "gemm_gelu",
+        "argmax_replicate", "argmax_replicate_odd", "gemm_tile", "gemm_k384", "gemm_qkv", "gemm_pair_small", "gemm_pair_qkv", "gemm_pair_big", "gemm_pair_vitb", "gemm_pair_gelu", "gemm_pair_resid", "gemm_gelu",
         "gemm_resid_k1536", "gemm_patch", "gemm_head", "gemm_big", "attn_1tile", "attn_ragged_small", "attn_2tiles",
         "attn_901", "attn_3601", "attn_vitb_901", "mlp_1block", "mlp_ragged", "mlp_multi", "mlp_pair_1block", "mlp_pair_ragged", "mlp_pair_multi",
     ]

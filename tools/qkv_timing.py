@@ -20,7 +20,7 @@ def main():
     p = lambda t: t.data_ptr()
     runs = {
         "single": lambda: lib.dinoseg_op_gemm(p(A), p(W), p(bias), p(out), M, N, K, N, 0, 0.125, N // 3, None, 0, 0, None),
-        "pair": lambda: lib.dinoseg_op_gemm_pair(p(A), p(W), p(bias), p(out), M, N, K, N, 0.125, N // 3, None),
+        "pair": lambda: lib.dinoseg_op_gemm_pair(p(A), p(W), p(bias), p(out), M, N, K, N, 0, 0.125, N // 3, None),
     }
     for rep in range(2):
         for name, fn in runs.items():
