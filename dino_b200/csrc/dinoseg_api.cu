@@ -393,7 +393,7 @@ struct dinoseg {
   float* pos_src = nullptr;
   __nv_bfloat16* pe_w = nullptr;
   float* pe_b = nullptr;
-  CUtensorMap tm_pe;
+  CUtensorMap tm_pe, tm_pe_p;       // (_p: 96-row half W tiles for the CTA-pair GEMM)
   std::vector<BlockW> blocks;
   float *norm_g = nullptr, *norm_b = nullptr;
   __nv_bfloat16* h1_w = nullptr;    // bf16x3 [H1, 3D]   = [hi | hi | lo]
@@ -644,6 +644,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   }
   if (rc == 0) {
     bool ok = make_tmap_2d(&h->tm_pe, h->pe_w, D, IM2COL_K3, IM2COL_K3, GEMM_BN);
+    ok &= make_tmap_2d(&h->tm_pe_p, h->pe_w, D, IM2COL_K3, IM2COL_K3, GEMM_BN / 2);
     ok &= make_tmap_2d(&h->tm_h1, h->h1_w, H1, 3 * D, 3 * D, GEMM_BN);
     ok &= make_tmap_2d(&h->tm_h2, h->h2_w, H2, 3 * kHeadPart, 3 * kHeadPart, GEMM_BN);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed for patch/head weights"; rc = -1; }
@@ -838,7 +839,13 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     p.a_wrap = IM2COL_KA;
     p.rows_per_batch = h->P; p.batches = batch; p.row_off = 1;   // out row = b*Ntok + 1 + t, + pos[1 + t]
     LaunchScope ls(h, K_GEMM_PATCH, s);
-    DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, w.tm_im2col, h->tm_pe, w.tm_x_patch, w.tm_pos_add, p, sms, s)); ++n;
+    if (h->gemm_pair &&
+        launch_gemm_pair<EPI_PATCH_F32>(w.tm_im2col, h->tm_pe_p, w.tm_x_patch, w.tm_pos_add, p, sms, s) != cudaSuccess) {
+      (void)cudaGetLastError();
+      h->gemm_pair = false;
+    }
+    if (!h->gemm_pair) DSG_CUDA(h, launch_gemm(EPI_PATCH_F32, w.tm_im2col, h->tm_pe, w.tm_x_patch, w.tm_pos_add, p, sms, s));
+    ++n;
   }
   if (stop == 1) { h->launches = n; return 0; }
 
