@@ -415,6 +415,7 @@ struct dinoseg {
   int debug_stop = 0;
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
+  int reverse_order = 1;            // GEMM / MLP kernels walk the rows last-to-first, LN / attention first-to-last
   bool gemm_pair = true;            // qkv GEMM as CTA pairs (cta_group::2)
   bool mlp_pair = false;       // ... as CTA pairs (cta_group::2), half the weights per SM
 
@@ -574,6 +575,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->device = device;
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
   h->mlp_pair = h->fused_mlp;       // CTA pairs measured 1.6 % faster than single CTAs (0.486 vs 0.494 ms per launch)
+  if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
     const int m = atoi(mode);
@@ -855,6 +857,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln1_g, b.ln1_b, w.abuf, M, D, eps, false, s)); ++n; }
     {
       GemmParams p = gp(3 * D, D, b.qkv_b);
+      p.reverse = h->reverse_order;              // LN1 wrote abuf first-to-last
       p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
       LaunchScope ls(h, K_GEMM_QKV, s);
       if (h->gemm_pair &&
@@ -874,6 +877,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     }
     {
       GemmParams p = gp(D, D, b.proj_b);
+      p.reverse = h->reverse_order;              // the attention kernel wrote abuf first-to-last
       LaunchScope ls(h, K_GEMM_PROJ, s);
       DSG_CUDA(h, launch_gemm(EPI_RESID_F32, w.tm_abuf, b.tm_proj, w.tm_x_out, w.tm_x_out, p, sms, s)); ++n;
     }
@@ -883,6 +887,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
       MlpParams p{};
       p.M = M; p.x = w.x; p.b1 = b.fc1_b; p.b2 = b.fc2_b;
+      p.reverse = h->reverse_order;              // LN2 wrote abuf first-to-last
       LaunchScope ls(h, K_MLP_FUSED, s);
       if (h->mlp_pair && launch_mlp_fused(w.tm_abuf, b.tm_fc1_h, b.tm_fc2_h, w.tm_x_out, p, sms, true, s) != cudaSuccess) {
         (void)cudaGetLastError();   // no 2-CTA clusters on this device / partition: same kernel, one CTA per row block
@@ -894,6 +899,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
       {
         GemmParams p = gp(HID, D, b.fc1_b);
+        p.reverse = h->reverse_order;            // LN2 wrote abuf first-to-last; fc2 then reads hid first-to-last
         LaunchScope ls(h, K_GEMM_FC1, s);
         if (h->gemm_pair &&
             launch_gemm_pair<EPI_GELU_BF16>(w.tm_abuf, b.tm_fc1_p, w.tm_hid_out, w.tm_hid_out, p, sms, s) != cudaSuccess) {

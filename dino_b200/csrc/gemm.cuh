@@ -48,6 +48,7 @@ struct GemmParams {
   float col_scale;
   int scale_cols;
   int split_part;       // EPI_RELU_SPLIT_BF16: width of each of the two output parts (multiple of 64)
+  int reverse;          // 1: row blocks are processed last to first (L2 reuse between consecutive kernels)
   int a_wrap;           // > 0: A has only a_wrap columns and the k index wraps (bf16x3 operand stored as [hi | lo])
   long long* timing;    // debug (DSG_GEMM_TIMING builds): [grid][3 roles][8] cycle totals
 };
@@ -182,19 +183,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar, 0));
     else mbar_arrive(bar);
   };
+  // p.reverse: walk the row blocks from the last to the first.  The kernels of a layer alternate direction so that
+  // each one starts with the rows its producer wrote last, which are still in L2 (the tensors are 2-4x the L2).
   auto tile_coords = [&](int t, int& mt, int& nt) {
+    int unit;                                      // row block (or row-block pair)
     if constexpr (RES_A) {
-      mt = (unit0 + (t / n_tiles) * ustride) * (PAIR ? 2 : 1) + int(cta_rank);
+      unit = unit0 + (t / n_tiles) * ustride;
       nt = t % n_tiles;
-    } else if constexpr (PAIR) {
+    } else {
       const int tile = unit0 + t * ustride;
       nt = tile % n_tiles;
-      mt = (tile / n_tiles) * 2 + int(cta_rank);
-    } else {
-      const int tile = int(blockIdx.x) + t * int(gridDim.x);
-      nt = tile % n_tiles;
-      mt = tile / n_tiles;
+      unit = tile / n_tiles;
     }
+    if (p.reverse) unit = m_units - 1 - unit;
+    mt = PAIR ? unit * 2 + int(cta_rank) : unit;
   };
 
   if (warp == 0 && elect_one()) {

@@ -32,6 +32,7 @@ struct MlpParams {
   const float* x;             // [M, 384] fp32 residual stream (read by the output warps; written through tmX)
   const float* b1;            // [1536]
   const float* b2;            // [384]
+  int reverse;                // 1: row blocks are processed last to first
   long long* timing;          // debug (DSG_MLP_TIMING): [grid][2 roles][8] cycle totals
 };
 
@@ -136,7 +137,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int unit0 = PAIR ? int(blockIdx.x) / 2 : int(blockIdx.x);
   const int unit_stride = PAIR ? int(gridDim.x) / 2 : int(gridDim.x);
   const int my_blocks = unit0 < units ? (units - 1 - unit0) / unit_stride + 1 : 0;
-  auto block_row0 = [&](int bi) { return ((unit0 + bi * unit_stride) * (PAIR ? 2 : 1) + int(cta_rank)) * MLP_BM; };
+  // p.reverse: row blocks last to first (the producer of A and x wrote its last rows most recently: L2 hits)
+  auto block_row0 = [&](int bi) {
+    int unit = unit0 + bi * unit_stride;
+    if (p.reverse) unit = units - 1 - unit;
+    return (unit * (PAIR ? 2 : 1) + int(cta_rank)) * MLP_BM;
+  };
   // arrive on a barrier of the leader CTA (the MMA issuer's side)
   auto arrive_leader = [&](uint64_t* bar) {
     if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar, 0));
