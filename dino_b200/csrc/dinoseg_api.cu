@@ -236,10 +236,10 @@ cudaError_t launch_gemm_pair(const CUtensorMap& a, const CUtensorMap& w, const C
                : launch_gemm_pair_t<EPI, false>(a, w, out, add, p, num_sms, s);
 }
 
-// The resident-A variant (K <= 384, several n-tiles) halves the L2 -> SM traffic per tile, but on B200 it
-// measured SLOWER than the streaming variant (qkv 0.235 vs 0.200 ms, fc1 0.366 vs 0.339 ms): the single
-// A buffer cannot be refilled early enough for the next row block (gemm.cuh).  It is kept selectable
-// (-DDSG_GEMM_RESA) for the follow-up with a deeper A ring; the default is the streaming variant.
+// Single-CTA launches.  The resident-A form (K <= 384, several n-tiles) measured SLOWER than streaming for single
+// CTAs (qkv 0.235 vs 0.200 ms: with the full 24 KB W tiles in the ring the single A buffer cannot be refilled early
+// enough) and is only compiled in with -DDSG_GEMM_RESA; as CTA pairs (12 KB half W tiles, launch_gemm_pair) it is
+// the fastest form and the default for the ViT-S qkv GEMM.
 template <int EPI>
 cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
                           const GemmParams& p, int num_sms, cudaStream_t s) {
