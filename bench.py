@@ -278,11 +278,20 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt_max = D.max_over_ranks(dt)
+        # what crosses PCIe device -> host per step: by default the low-res maps, which the library's host threads
+        # expand into the int64 [480,480] maps inside the same call (np.kron of the reference); with host_expand off
+        # the maps are replicated on the GPU and copied out whole
+        from dino_b200 import _lib as _L
+        expand = _L.load().dinoseg_get_host_expand(model._handle) == 1
+        d2h = int((B * g * g if expand else out.size * 8) * world)
+        tail = ("low-res maps D2H, expanded to int64 label maps by the library's host threads"
+                if expand else "int64 maps replicated on the GPU and copied out whole")
         e2e = {"value": world * B * args.steps / dt_max, "unit": UNIT,
                "h2d_bytes_per_step": int(frames_host.numel() * 4 * world),
-               "d2h_bytes_per_step": int(out.size * 8 * world),
+               "d2h_bytes_per_step": d2h, "host_label_bytes_per_step": int(out.size * 8 * world),
                "api": "DINOSeg.predict_batch(pinned host fp32 frames) -> int64 host label maps (dinoseg_predict_host: "
-                      "H2D + forward + D2H + sync inside the timed region, pipelined over ~10-frame chunks on 3 streams)"}
+                      "H2D + forward + D2H + sync inside the timed region, pipelined over ~10-frame chunks on 3 streams; "
+                      + tail + ")"}
     # ---- the same from RAW camera frames (uint8 640x480 RGB, as DINOSeg.predict receives them): resize + normalise on
     # the GPU as well; informational, the contract's `e2e` is the fp32 path above ----
     e2e_u8 = None
@@ -299,7 +308,7 @@ def main():
         torch.cuda.synchronize()
         dt_max = D.max_over_ranks(time.perf_counter() - t0)
         e2e_u8 = {"value": world * B * args.steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": int(raw.numel() * world),
-                  "d2h_bytes_per_step": int(out_host.numel() * 8 * world),
+                  "d2h_bytes_per_step": d2h, "host_label_bytes_per_step": int(out_host.numel() * 8 * world),
                   "api": "DINOSeg.predict_batch_u8(pinned host uint8 640x480 RGB frames) -> int64 host label maps "
                          "(cv2-exact bilinear resize + normalisation fused into the patch embed on the GPU)"}
     t_wall2 = time.time()

@@ -61,6 +61,8 @@ SIGNATURES = {
                                     C.c_int, C.c_void_p]),
     "dinoseg_op_gemm_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "dinoseg_set_host_expand": (C.c_int, [C.c_void_p, C.c_int]),
+    "dinoseg_get_host_expand": (C.c_int, [C.c_void_p]),
     "dinoseg_half_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dinoseg_set_fused_mlp": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

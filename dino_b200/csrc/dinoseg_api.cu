@@ -11,8 +11,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <sched.h>
+#include <emmintrin.h>
 #include <set>
 #include <string>
 #include <vector>
@@ -370,6 +376,79 @@ struct WorkBufs {
 
 // predict_host pipeline lane: own stream, device staging and workspace, so that the copies of one
 // chunk of frames overlap the kernels of another
+// Worker threads of the host entry points (label-map expansion, see predict_host_impl).
+class HostPool {
+ public:
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { run(); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+    cv_.notify_all();
+    for (std::thread& t : threads_) t.join();
+  }
+  void submit(std::function<void()> f) {
+    { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(f)); ++pending_; }
+    cv_.notify_one();
+  }
+  void wait_all() {
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+  }
+  int size() const { return int(threads_.size()); }
+
+ private:
+  void run() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        f = std::move(q_.front());
+        q_.pop_front();
+      }
+      f();
+      { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::deque<std::function<void()>> q_;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+// predict() tail on the host (reference pl_torch_modules.py:297-298: np.kron(low, ones((p, p)))): one frame's low-res
+// map [g, g] u8 -> int64 [g*p, g*p].  One label row is built in a small buffer and written p times with streaming
+// (non-temporal) stores: the maps are write-only here, and without the read-for-ownership traffic of ordinary
+// stores the expansion costs half the memory bandwidth.
+void expand_labels_host(const uint8_t* low, int64_t* out, int g, int p) {
+  const size_t W = size_t(g) * p;                  // <= 480
+  alignas(16) int64_t row[480];
+  const bool nt = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (W % 2 == 0);
+  for (int i = 0; i < g; ++i) {
+    const uint8_t* lr = low + size_t(i) * g;
+    for (int j = 0; j < g; ++j) {
+      const int64_t v = lr[j];
+      int64_t* d = row + size_t(j) * p;
+      for (int k = 0; k < p; ++k) d[k] = v;
+    }
+    for (int r = 0; r < p; ++r) {
+      int64_t* dst = out + (size_t(i) * p + r) * W;
+      if (nt) {
+        const __m128i* src = reinterpret_cast<const __m128i*>(row);
+        __m128i* d = reinterpret_cast<__m128i*>(dst);
+        for (size_t k = 0; k < W / 2; ++k) _mm_stream_si128(d + k, _mm_load_si128(src + k));
+      } else {
+        memcpy(dst, row, W * sizeof(int64_t));
+      }
+    }
+  }
+  if (nt) _mm_sfence();
+}
+
 struct HostLane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -431,6 +510,13 @@ struct dinoseg {
   HostLane lanes[kLanes];
   cudaEvent_t host_start = nullptr;
   int host_chunk = 0;               // frames per pipeline chunk; 0 = automatic (see pick_host_chunk)
+  // host label maps: 1 = copy the low-res maps (g*g bytes per frame) to the host and expand them to int64 there with
+  // worker threads (what the reference does with np.kron); 0 = replicate on the GPU and copy 8*(g*p)^2 bytes per frame
+  int host_expand = 1;
+  HostPool* pool = nullptr;
+  uint8_t* low_stage = nullptr;     // pinned [batch, g*g]
+  size_t low_stage_cap = 0;
+  std::vector<cudaEvent_t> chunk_done;
 };
 
 namespace {
@@ -575,6 +661,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->device = device;
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
   h->mlp_pair = h->fused_mlp;       // CTA pairs measured 1.6 % faster than single CTAs (0.486 vs 0.494 ms per launch)
+  if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
@@ -675,6 +762,9 @@ void dinoseg_destroy(dinoseg_t* h) {
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   if (h->host_start) cudaEventDestroy(h->host_start);
+  delete h->pool;
+  if (h->low_stage) cudaFreeHost(h->low_stage);
+  for (cudaEvent_t e : h->chunk_done) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
@@ -1037,6 +1127,36 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
   }
   const int nchunks = int(plan.size());
   const int nlanes = nchunks < dinoseg::kLanes ? nchunks : dinoseg::kLanes;
+  const bool want_labels = host_labels && label_elems;
+  // Label maps: the int64 [g*p, g*p] map is 512x the size of the low-res map it replicates.  With host_expand the
+  // GPU ships the low-res maps (3.6 KB per frame at 480 px) and worker threads expand them into the caller's buffer
+  // while later chunks are still computing, instead of 1.84 MB per frame over PCIe.
+  const bool expand = want_labels && h->host_expand != 0;
+  if (expand) {
+    if (!h->pool) {
+      int cpus = 0;
+      cpu_set_t set;
+      if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+      if (cpus <= 0) cpus = int(std::thread::hardware_concurrency());
+      const char* lw = getenv("LOCAL_WORLD_SIZE");          // torchrun: ranks sharing this host's cores
+      const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+      int n = cpus / ranks;
+      if (const char* e = getenv("DINOSEG_HOST_THREADS")) n = atoi(e);
+      n = n < 1 ? 1 : (n > 8 ? 8 : n);
+      h->pool = new HostPool(n);
+    }
+    const size_t need = size_t(batch) * h->P;
+    if (need > h->low_stage_cap) {
+      if (h->low_stage) { cudaFreeHost(h->low_stage); h->low_stage = nullptr; h->low_stage_cap = 0; }
+      DSG_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&h->low_stage), need, cudaHostAllocDefault));
+      h->low_stage_cap = need;
+    }
+    while (int(h->chunk_done.size()) < nchunks) {
+      cudaEvent_t e;
+      DSG_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->chunk_done.push_back(e);
+    }
+  }
   for (int k = 0; k < nlanes; ++k) {
     HostLane& l = h->lanes[k];
     if (!l.stream) DSG_CUDA(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
@@ -1045,7 +1165,7 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
     DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.frames), &l.frames_cap, size_t(chunk) * frame_bytes));
     DSG_CUDA(h, grow(l, &l.ws, &l.ws_cap, wbytes));
     DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.lowres), &l.lowres_cap, size_t(chunk) * h->P));
-    if (host_labels && label_elems)
+    if (want_labels && !expand)
       DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.labels), &l.labels_cap, size_t(chunk) * label_elems * sizeof(int64_t)));
     if (l.ws_cap != ws_before) l.bufs.base = nullptr;
   }
@@ -1061,18 +1181,41 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
                                 size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, l.stream));
     if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
     if (forward_impl(h, l.bufs, pp ? nullptr : l.frames, pp ? reinterpret_cast<const uint8_t*>(l.frames) : nullptr, pp, nb,
-                     nullptr, l.lowres, (host_labels && label_elems) ? l.labels : nullptr, l.stream) != 0)
+                     nullptr, l.lowres, (want_labels && !expand) ? l.labels : nullptr, l.stream) != 0)
       return -1;
+    if (expand) {
+      DSG_CUDA(h, cudaMemcpyAsync(h->low_stage + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
+                                  l.stream));
+      DSG_CUDA(h, cudaEventRecord(h->chunk_done[c], l.stream));
+      continue;
+    }
     if (host_lowres)
       DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
                                   l.stream));
-    if (host_labels && label_elems)
+    if (want_labels)
       DSG_CUDA(h, cudaMemcpyAsync(host_labels + size_t(f0) * label_elems, l.labels,
                                   size_t(nb) * label_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
   }
   for (int k = 0; k < nlanes; ++k) {
     DSG_CUDA(h, cudaEventRecord(h->lanes[k].done, h->lanes[k].stream));
     DSG_CUDA(h, cudaStreamWaitEvent(s, h->lanes[k].done, 0));   // later work on the caller's stream is ordered after us
+  }
+  if (expand) {
+    // chunk by chunk, as the low-res maps arrive: one expansion task per frame
+    const int g = h->g, prep = h->p_rep;
+    const size_t P = h->P;
+    f0 = 0;
+    for (int c = 0; c < nchunks; f0 += plan[c], ++c) {
+      if (plan[c] <= 0) continue;
+      DSG_CUDA(h, cudaEventSynchronize(h->chunk_done[c]));
+      if (host_lowres) memcpy(host_lowres + size_t(f0) * P, h->low_stage + size_t(f0) * P, size_t(plan[c]) * P);
+      for (int i = 0; i < plan[c]; ++i) {
+        const uint8_t* low = h->low_stage + size_t(f0 + i) * P;
+        int64_t* out = host_labels + size_t(f0 + i) * label_elems;
+        h->pool->submit([low, out, g, prep] { expand_labels_host(low, out, g, prep); });
+      }
+    }
+    h->pool->wait_all();
   }
   for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamSynchronize(h->lanes[k].stream));
   return 0;
@@ -1114,6 +1257,14 @@ int dinoseg_forward_u8(dinoseg_t* h, const uint8_t* frames, int batch, int src_h
   if (bind_workspace(h, h->user, workspace, workspace_bytes, batch) != 0) return -1;
   return forward_impl(h, h->user, nullptr, frames, &pp, batch, logprobs, lowres, labels, static_cast<cudaStream_t>(stream));
 }
+
+int dinoseg_set_host_expand(dinoseg_t* h, int on) {
+  if (!h || on < 0 || on > 1) return -1;
+  h->host_expand = on;
+  return 0;
+}
+
+int dinoseg_get_host_expand(const dinoseg_t* h) { return h ? h->host_expand : -1; }
 
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk) {
   if (!h || frames_per_chunk < 0) return -1;

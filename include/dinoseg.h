@@ -97,6 +97,13 @@ int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames_u8, int bat
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 
+/* How the host entry points produce the int64 label maps.  1 (default): the low-res maps (g*g bytes per frame) are copied
+ * to the host and expanded there by worker threads into the caller's buffer while later chunks compute - what the
+ * reference does with np.kron (pl_torch_modules.py:297-298), 512x fewer bytes over PCIe.  0: the maps are replicated on
+ * the GPU and copied out whole (8*(g*p)^2 bytes per frame).  Both produce identical bytes. */
+int dinoseg_set_host_expand(dinoseg_t* h, int on);
+int dinoseg_get_host_expand(const dinoseg_t* h);
+
 /* CLS-query attention of the last kept block: attn [batch, heads, N] fp32 = softmax(q_cls k^T * dh^-0.5) per head,
  * i.e. row 0 of what VisionTransformer.get_last_selfattention returns (vision_transformer.py:273-280) — the only
  * row its caller reads (visualize_attention.py:46-54).  frames: device fp32 [batch,3,r,r]. */

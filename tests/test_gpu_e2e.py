@@ -254,6 +254,16 @@ def test_host_entry_point_matches_device_path():
     low_host = m.predict_batch(x, output="lowres")            # pageable memory works too
     assert isinstance(lab_host, np.ndarray) and lab_host.dtype == np.int64
     assert (lab_host == lab_dev.cpu().numpy()).all() and (low_host == low_dev.cpu().numpy()).all()
+    # the two ways of producing host label maps (low-res D2H + expansion by the library's host threads, the default;
+    # GPU replication + D2H of the whole int64 maps) give the same bytes
+    lib = _lib.load()
+    assert lib.dinoseg_get_host_expand(m._handle) == 1
+    assert lib.dinoseg_set_host_expand(m._handle, 0) == 0
+    lab_dma = m.predict_batch(x.pin_memory(), output="labels")
+    assert lib.dinoseg_set_host_expand(m._handle, 1) == 0
+    assert (lab_dma == lab_host).all()
+    big = synthetic.make_frames(23, 240, seed=3)               # several chunks, ragged first / last chunk
+    assert (m.predict_batch(big.pin_memory(), output="labels") == m.predict_batch(big.cuda(), output="labels").cpu().numpy()).all()
 
 
 @pytest.mark.parametrize("hw,res", [((480, 640), 480), ((480, 640), 240), ((360, 500), 480), ((480, 480), 480)])
