@@ -52,7 +52,38 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = auto (bounded by ~20 s)")
     ap.add_argument("--kernels", action="store_true", help="add a per-kernel-kind breakdown (extra profiled pass)")
+    ap.add_argument("--stall-limit", type=float, default=0.0,
+                    help="seconds after which a run that has not finished is aborted with an error line instead of "
+                         "hanging the box (0 = 600 s + 2 s per step)")
     return ap.parse_args()
+
+
+def arm_stall_watchdog(args):
+    """A stalled run (GPU kernel that never returns, wedged collective, ...) must END: after the limit the process
+    prints an error line and exits hard (os._exit tears the CUDA context down, which kills whatever is running)."""
+    import threading
+    limit = args.stall_limit if args.stall_limit > 0 else 600.0 + 2.0 * (args.steps + args.warmup)
+
+    def fire():
+        sys.stderr.write(f"bench.py: no result after {limit:.0f} s - aborting\n")
+        sys.stderr.flush()
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"error": f"stalled: no result after {limit:.0f} s", "impl": args.impl}), flush=True)
+        os._exit(3)
+
+    t = threading.Timer(limit, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
+def kernel_options(model):
+    """Opt-in library switches active in this run (DINOSEG_PAIR / DINOSEG_HOST_EXPAND or the C-ABI setters)."""
+    from dino_b200 import _lib
+    lib = _lib.load()
+    pair = lib.dinoseg_get_pair_kernels(model._handle)
+    return {"cta_pair_gemms": bool(pair & 1), "cta_pair_fused_mlp": bool(pair & 2),
+            "host_label_expansion": lib.dinoseg_get_host_expand(model._handle) == 1}
 
 
 def load_peaks():
@@ -202,6 +233,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    arm_stall_watchdog(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -356,7 +388,8 @@ def main():
         "config": {"workload": workload_name(args), "global_batch": world * B, "weights": f"random init ({args.variant})",
                    "parallelism": f"replicas x{world} (frames sharded, no collective)", "host_cores_bound_per_rank": bound_cores,
                    "l2": "inputs+workspace per step (>1.5 GB) exceed the 126 MB L2; no explicit flush",
-                   "arithmetic": "bf16 tensor-core operands, fp32 accumulate / residual stream / LN / softmax / GELU"},
+                   "arithmetic": "bf16 tensor-core operands, fp32 accumulate / residual stream / LN / softmax / GELU",
+                   "kernel_options": kernel_options(model)},
         "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline,
         "whole_step": {"gflop_per_frame": F / 1e9, "achieved_tflops_per_gpu": step_tf, "frac_of_peak": step_tf / peak_tf},

@@ -61,6 +61,8 @@ SIGNATURES = {
                                     C.c_int, C.c_void_p]),
     "dinoseg_op_gemm_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "dinoseg_set_pair_kernels": (C.c_int, [C.c_void_p, C.c_int]),
+    "dinoseg_get_pair_kernels": (C.c_int, [C.c_void_p]),
     "dinoseg_set_host_expand": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_get_host_expand": (C.c_int, [C.c_void_p]),
     "dinoseg_half_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

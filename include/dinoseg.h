@@ -97,12 +97,18 @@ int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames_u8, int bat
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 
-/* How the host entry points produce the int64 label maps.  1 (default): the low-res maps (g*g bytes per frame) are copied
- * to the host and expanded there by worker threads into the caller's buffer while later chunks compute - what the
- * reference does with np.kron (pl_torch_modules.py:297-298), 512x fewer bytes over PCIe.  0: the maps are replicated on
- * the GPU and copied out whole (8*(g*p)^2 bytes per frame).  Both produce identical bytes. */
+/* How the host entry points produce the int64 label maps.  0 (default): the maps are replicated on the GPU and copied
+ * out whole (8*(g*p)^2 bytes per frame).  1: the low-res maps (g*g bytes per frame) are copied to the host and expanded
+ * there by worker threads into the caller's buffer while later chunks compute - what the reference does with np.kron
+ * (pl_torch_modules.py:297-298), 512x fewer bytes over PCIe (+2.5 % e2e on one GPU, +4 % on eight).  Identical bytes. */
 int dinoseg_set_host_expand(dinoseg_t* h, int on);
 int dinoseg_get_host_expand(const dinoseg_t* h);
+
+/* CTA-pair (tcgen05 cta_group::2) forms of the fused MLP and of the qkv / patch-embed (ViT-B: fc1, fc2) GEMMs: M = 256
+ * MMAs issued by the leader CTA of a 2-CTA cluster, weights split between the two SMs.  Bit-identical results, about
+ * +2 % frames/s.  Off by default (also DINOSEG_PAIR=1 in the environment at dinoseg_create time). */
+int dinoseg_set_pair_kernels(dinoseg_t* h, int on);
+int dinoseg_get_pair_kernels(const dinoseg_t* h);   /* bit 0: GEMMs, bit 1: fused MLP */
 
 /* CLS-query attention of the last kept block: attn [batch, heads, N] fp32 = softmax(q_cls k^T * dh^-0.5) per head,
  * i.e. row 0 of what VisionTransformer.get_last_selfattention returns (vision_transformer.py:273-280) — the only
@@ -165,7 +171,7 @@ int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const floa
 int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                       const float* b2, int M, int pair, void* stream);
 /* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel, one CTA per row block; 2: fused MLP kernel run by CTA pairs
- * (cta_group::2) - the default where the fused kernel applies (embed_dim 384, mlp_hidden 1536) */
+ * (cta_group::2); 1 is the default where the fused kernel applies (embed_dim 384, mlp_hidden 1536) */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
                          float eps, void* stream);

@@ -254,16 +254,33 @@ def test_host_entry_point_matches_device_path():
     low_host = m.predict_batch(x, output="lowres")            # pageable memory works too
     assert isinstance(lab_host, np.ndarray) and lab_host.dtype == np.int64
     assert (lab_host == lab_dev.cpu().numpy()).all() and (low_host == low_dev.cpu().numpy()).all()
-    # the two ways of producing host label maps (low-res D2H + expansion by the library's host threads, the default;
-    # GPU replication + D2H of the whole int64 maps) give the same bytes
+    # the two ways of producing host label maps (GPU replication + D2H of the whole int64 maps, the default; low-res
+    # D2H + expansion by the library's host threads) give the same bytes
     lib = _lib.load()
-    assert lib.dinoseg_get_host_expand(m._handle) == 1
-    assert lib.dinoseg_set_host_expand(m._handle, 0) == 0
-    lab_dma = m.predict_batch(x.pin_memory(), output="labels")
+    assert lib.dinoseg_get_host_expand(m._handle) == 0
     assert lib.dinoseg_set_host_expand(m._handle, 1) == 0
-    assert (lab_dma == lab_host).all()
+    lab_exp = m.predict_batch(x.pin_memory(), output="labels")
     big = synthetic.make_frames(23, 240, seed=3)               # several chunks, ragged first / last chunk
-    assert (m.predict_batch(big.pin_memory(), output="labels") == m.predict_batch(big.cuda(), output="labels").cpu().numpy()).all()
+    big_exp = m.predict_batch(big.pin_memory(), output="labels")
+    assert lib.dinoseg_set_host_expand(m._handle, 0) == 0
+    assert (lab_exp == lab_host).all()
+    assert (big_exp == m.predict_batch(big.cuda(), output="labels").cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("arch,res", [("vit_small", 240), ("vit_small", 224), ("vit_base", 64)])
+def test_pair_kernels_are_bit_identical(arch, res):
+    """The CTA-pair (tcgen05 cta_group::2) forms of the fused MLP and of the qkv / patch-embed / fc1 / fc2 GEMMs are
+    opt-in; they run the same MMAs per output row and must reproduce the default kernels bit for bit."""
+    lib = _lib.load()
+    m, cfg, sd = _model(arch, 2, 11, "trained_like")
+    x = synthetic.make_frames(3, res, seed=4).cuda()
+    a = m(x).clone()
+    assert lib.dinoseg_set_pair_kernels(m._handle, 1) == 0
+    b = m(x).clone()
+    assert lib.dinoseg_set_pair_kernels(m._handle, 0) == 0
+    c = m(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
 
 
 @pytest.mark.parametrize("hw,res", [((480, 640), 480), ((480, 640), 240), ((360, 500), 480), ((480, 480), 480)])

@@ -192,6 +192,16 @@ def test_bench_reference_arm_contract():
     assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["value"] == r["value"]
 
 
+def test_bench_stall_watchdog_ends_the_run():
+    """A run that does not finish inside --stall-limit prints an error line and exits with code 3 instead of hanging."""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "50",
+                        "--warmup", "1", "--stall-limit", "2"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 3, (p.returncode, p.stderr[-500:])
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert "stalled" in r["error"]
+
+
 def test_product_code_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under dino_b200/ or dt_segmentation/ may use it."""
     for pkg in ("dino_b200", "dt_segmentation"):
