@@ -21,7 +21,8 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
-            item.add_marker(pytest.mark.timeout(300))
+            # method 'thread': a test stuck inside a CUDA call never returns to Python, so a signal would not fire
+            item.add_marker(pytest.mark.timeout(300, method="thread"))
 
 
 @pytest.fixture(scope="session")
