@@ -1271,6 +1271,13 @@ int dinoseg_set_pair_kernels(dinoseg_t* h, int on) {
   return 0;
 }
 
+int dinoseg_expand_labels_host(const uint8_t* lowres, int batch, int g, int p, int64_t* labels) {
+  if (!lowres || !labels || batch <= 0 || g <= 0 || p <= 0 || size_t(g) * p > 480) return -1;
+  const size_t W = size_t(g) * p;
+  for (int b = 0; b < batch; ++b) expand_labels_host(lowres + size_t(b) * g * g, labels + size_t(b) * W * W, g, p);
+  return 0;
+}
+
 int dinoseg_get_pair_kernels(const dinoseg_t* h) { return h ? (h->gemm_pair ? 1 : 0) | (h->mlp_pair ? 2 : 0) : -1; }
 
 int dinoseg_set_host_expand(dinoseg_t* h, int on) {

@@ -103,6 +103,9 @@ int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
  * (pl_torch_modules.py:297-298), 512x fewer bytes over PCIe (+2.5 % e2e on one GPU, +4 % on eight).  Identical bytes. */
 int dinoseg_set_host_expand(dinoseg_t* h, int on);
 int dinoseg_get_host_expand(const dinoseg_t* h);
+/* The host-side expansion itself (pure CPU, no device needed): lowres host uint8 [batch, g, g] -> labels host int64
+ * [batch, g*p, g*p], out[b, y, x] = lowres[b, y / p, x / p] (np.kron with ones((p, p))); g*p <= 480. */
+int dinoseg_expand_labels_host(const uint8_t* lowres, int batch, int g, int p, int64_t* labels);
 
 /* CTA-pair (tcgen05 cta_group::2) forms of the fused MLP and of the qkv / patch-embed (ViT-B: fc1, fc2) GEMMs: M = 256
  * MMAs issued by the leader CTA of a 2-CTA cluster, weights split between the two SMs.  Bit-identical results, about

@@ -192,6 +192,26 @@ def test_bench_reference_arm_contract():
     assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["value"] == r["value"]
 
 
+@pytest.mark.parametrize("g,p,offset", [(60, 8, 0), (30, 16, 0), (62, 7, 0), (3, 160, 0), (1, 480, 0), (5, 96, 8)])
+def test_host_label_expansion_matches_np_kron(g, p, offset):
+    """The host-side label expansion of the library (used by dinoseg_set_host_expand) == np.kron(low, ones((p, p))),
+    reference pl_torch_modules.py:297-298 - including a 7-pixel replication (odd row length: no streaming stores) and
+    an output buffer that is only 8-byte aligned."""
+    import ctypes as C
+    from dino_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(g * 1000 + p)
+    low = rng.integers(0, 256, size=(3, g, g), dtype=np.uint8)
+    w = g * p
+    buf = np.full(3 * w * w + 2, -7, dtype=np.int64)
+    out = buf[offset // 8: offset // 8 + 3 * w * w].reshape(3, w, w)
+    rc = lib.dinoseg_expand_labels_host(low.ctypes.data_as(C.c_void_p), 3, g, p, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    ref = np.stack([np.kron(low[b].astype(np.int64), np.ones((p, p), dtype=np.int64)) for b in range(3)])
+    assert np.array_equal(out, ref)
+    assert (buf[3 * w * w + offset // 8:] == -7).all()
+
+
 def test_bench_stall_watchdog_ends_the_run():
     """A run that does not finish inside --stall-limit prints an error line and exits with code 3 instead of hanging."""
     import json
