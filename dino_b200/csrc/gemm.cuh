@@ -282,6 +282,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           GEMM_T(2);
         }
       }
+#ifdef DSG_PAIR_TAIL
+      // Producer tail (NOT yet validated on hardware, hence opt-in at compile time): the
+      // leader's last multicast commits on this CTA's stage-empty barriers are otherwise never waited for, and the
+      // CTA must not exit while one of them may still be in flight towards its shared memory.
+      if constexpr (PAIR) {
+        for (uint32_t i = 0; i < uint32_t(STAGES) && i < kc; ++i) {
+          const uint32_t idx = kc - 1 - i;
+          mbar_wait(&empty_bar[idx % STAGES], (idx / STAGES) & 1);
+        }
+        if constexpr (RES_A) {
+          if (my_tiles > 0) {
+            const int last_mi = my_tiles / n_tiles - 1;
+            for (int kb = 0; kb < num_kb; ++kb) mbar_wait(&a_empty[kb], last_mi & 1);
+          }
+        }
+      }
+#endif
       GEMM_T_DUMP(0);
     }
   } else if (warp == 1) {
