@@ -82,7 +82,7 @@ struct AttItem {
   bool act1;     // warpgroup 1 has work
   bool dual;     // two K/V streams
 };
-__device__ __forceinline__ AttItem att_decode(const AttnParams& p, int item) {
+__host__ __device__ __forceinline__ AttItem att_decode(const AttnParams& p, int item) {
   AttItem I;
   I.act1 = true;
   I.dual = false;

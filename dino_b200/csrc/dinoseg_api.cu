@@ -273,6 +273,14 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& a, const CUtensorMap& w, con
 }
 
 
+// work-item plan of the attention kernel (see att_decode): lone last query tiles are paired across heads
+void attn_plan_items(AttnParams& p) {
+  const int q_tiles = (p.N + ATT_BM - 1) / ATT_BM;
+  p.full_pairs = q_tiles / 2;
+  p.lone = q_tiles & 1;
+  p.num_items = p.B * p.H * p.full_pairs + (p.lone ? (p.B * p.H + 1) / 2 : 0);
+}
+
 cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
   p.timing = g_attn_timing;
   auto kern = attn_fwd_kernel<kAttnStages>;
@@ -285,10 +293,7 @@ cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, 
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  const int q_tiles = (p.N + ATT_BM - 1) / ATT_BM;
-  p.full_pairs = q_tiles / 2;
-  p.lone = q_tiles & 1;
-  p.num_items = p.B * p.H * p.full_pairs + (p.lone ? (p.B * p.H + 1) / 2 : 0);   // lone last tiles are paired across heads
+  attn_plan_items(p);
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
   kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
   return cudaGetLastError();
@@ -1381,6 +1386,21 @@ int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* 
                         : epi == EPI_GELU_BF16 ? launch_gemm_pair<EPI_GELU_BF16>(ta, tw, to, to, p, sms, s)
                                                : launch_gemm_pair<EPI_RESID_F32>(ta, tw, to, to, p, sms, s);
   return e == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_debug_attn_items(int B, int H, int N, int32_t* items, int max_items) {
+  if (B <= 0 || H <= 0 || N <= 0) return -1;
+  AttnParams p{};
+  p.B = B; p.H = H; p.N = N; p.D = H * ATT_DH;
+  attn_plan_items(p);
+  if (!items) return p.num_items;
+  if (max_items < p.num_items) return -1;
+  for (int i = 0; i < p.num_items; ++i) {
+    const AttItem I = att_decode(p, i);
+    int32_t* o = items + size_t(i) * 6;
+    o[0] = I.bh[0]; o[1] = I.q0[0]; o[2] = I.bh[1]; o[3] = I.q0[1]; o[4] = I.act1 ? 1 : 0; o[5] = I.dual ? 1 : 0;
+  }
+  return p.num_items;
 }
 
 int dinoseg_debug_set_attn_timing(long long* dev_ptr) {

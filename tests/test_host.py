@@ -212,6 +212,36 @@ def test_host_label_expansion_matches_np_kron(g, p, offset):
     assert (buf[3 * w * w + offset // 8:] == -7).all()
 
 
+@pytest.mark.parametrize("B,H,N", [(64, 6, 3601), (1, 6, 3601), (3, 6, 785), (2, 6, 901), (1, 1, 65), (3, 1, 129),
+                                   (5, 3, 300), (1, 12, 3601), (7, 1, 1), (2, 12, 14401)])
+def test_attention_work_items_cover_every_query_tile_once(B, H, N):
+    """The attention kernel's work-item plan (regular items = two query tiles of one head, dual tail items = the lone
+    last tiles of two heads, single tail item for an odd number of heads): every (frame*H + head, query tile) is
+    covered exactly once, and a dual item directly follows the regular items of its two heads."""
+    import ctypes as C
+    from dino_b200 import _lib
+    lib = _lib.load()
+    n = lib.dinoseg_debug_attn_items(B, H, N, None, 0)
+    q_tiles = (N + 127) // 128
+    bh = B * H
+    assert n == bh * (q_tiles // 2) + ((bh + 1) // 2 if q_tiles % 2 else 0)
+    buf = np.zeros((n, 6), dtype=np.int32)
+    assert lib.dinoseg_debug_attn_items(B, H, N, buf.ctypes.data_as(C.c_void_p), n) == n
+    seen = {}
+    for i, (bh0, q0, bh1, q1, act1, dual) in enumerate(buf.tolist()):
+        assert 0 <= bh0 < bh and q0 % 128 == 0 and 0 <= q0 < N
+        seen[(bh0, q0 // 128)] = seen.get((bh0, q0 // 128), 0) + 1
+        if act1:
+            assert 0 <= bh1 < bh and q1 % 128 == 0 and 0 <= q1 < N
+            seen[(bh1, q1 // 128)] = seen.get((bh1, q1 // 128), 0) + 1
+        assert bool(dual) == (bool(act1) and bh0 != bh1)
+        if dual:                                     # K/V locality: the item before it belongs to one of its heads
+            assert q0 == q1 == (q_tiles // 2) * 256 and bh1 == bh0 + 1
+            if q_tiles > 1:
+                assert buf[i - 1][0] == bh1
+    assert len(seen) == bh * q_tiles and all(v == 1 for v in seen.values())
+
+
 def test_bench_stall_watchdog_ends_the_run():
     """A run that does not finish inside --stall-limit prints an error line and exits with code 3 instead of hanging."""
     import json
