@@ -252,6 +252,20 @@ def test_bench_stall_watchdog_ends_the_run():
     assert "stalled" in r["error"]
 
 
+def test_bench_supervisor_retries_a_stalled_single_gpu_run_once():
+    """Single-GPU runs execute in a child process; a child that stalls is killed, the run repeated once, and after a
+    second stall the parent reports the failure instead of hanging."""
+    import json
+    env = dict(os.environ, DINOSEG_BENCH_TEST_STALL="1")
+    env.pop("WORLD_SIZE", None)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--stall-limit", "1.5"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert p.returncode == 3, (p.returncode, p.stderr[-500:])
+    assert p.stderr.count("no result after") == 2 and "retrying once" in p.stderr
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert "failed" in r["error"] and "stalled" in r["error"]
+
+
 def test_product_code_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under dino_b200/ or dt_segmentation/ may use it."""
     for pkg in ("dino_b200", "dt_segmentation"):
