@@ -1142,9 +1142,9 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
   // Label maps: the int64 [g*p, g*p] map is 512x the size of the low-res map it replicates.  With host_expand the
   // GPU ships the low-res maps (3.6 KB per frame at 480 px) and worker threads expand them into the caller's buffer
   // while later chunks are still computing, instead of 1.84 MB per frame over PCIe.
-  const bool expand = want_labels && h->host_expand != 0;
-  if (expand) {
-    if (!h->pool) {
+  bool expand = want_labels && h->host_expand != 0;
+  if (expand && !h->pool) {
+    {
       int cpus = 0;
       cpu_set_t set;
       if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
@@ -1154,8 +1154,16 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
       int n = cpus / ranks;
       if (const char* e = getenv("DINOSEG_HOST_THREADS")) n = atoi(e);
       n = n < 1 ? 1 : (n > 8 ? 8 : n);
-      h->pool = new HostPool(n);
+      try {
+        h->pool = new HostPool(n);
+      } catch (...) {                              // no threads to be had: GPU replication + whole-map copies
+        h->pool = nullptr;
+        h->host_expand = 0;
+        expand = false;
+      }
     }
+  }
+  if (expand) {
     const size_t need = size_t(batch) * h->P;
     if (need > h->low_stage_cap) {
       if (h->low_stage) { cudaFreeHost(h->low_stage); h->low_stage = nullptr; h->low_stage_cap = 0; }
