@@ -5,10 +5,14 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
 
 A "step" is one pass of the hot path (ViT-S/8 truncated to 3 blocks at 480 px -> MLP head ->
-argmax -> 480x480 int64 label maps) over one batch of 64 synthetic frames per GPU
-(BASELINE.json configs[1]; configs[2] = the same per-GPU batch on 2/4/8 GPUs, 512 frames at 8).
+argmax -> 480x480 int64 label maps) over one batch of synthetic frames:
+  N = 1 : 64 frames (BASELINE.json configs[1]);
+  N > 1 : 512 frames sharded across the N GPUs, 256 / 128 / 64 per GPU (configs[2]; `scaling: "strong"`).
+`--batch B` fixes the per-GPU batch instead (weak scaling), `--global-batch G` the global one.
 Frames shard across ranks as independent replicas: no collective on the data path; NCCL is only
 used for the barrier around the timed region and the max-over-ranks of the device time.
+At N = 1 the line also carries `extra_configs`: BASELINE configs[3] (960 px, 16 frames) and configs[4]'s per-GPU
+shape (ViT-B/8, 4 blocks, 480 px, 32 frames), measured in the same run (device-resident frames, CUDA events).
 
 Output: ONE JSON line on rank 0 (see the keys below).  `value` is timed with CUDA events with the
 frames already resident in HBM; `e2e` is the same metric through the public API
@@ -43,7 +47,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (0 = 64 on one GPU, 512 / N on N GPUs)")
+    ap.add_argument("--global-batch", type=int, default=0, help="frames per step over all GPUs (overrides --batch)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the 960 px / ViT-B side measurements (N = 1)")
     ap.add_argument("--res", type=int, default=480)
     ap.add_argument("--arch", default="vit_small")
     ap.add_argument("--n-blocks", type=int, default=3)
@@ -55,7 +61,18 @@ def parse_args():
     ap.add_argument("--stall-limit", type=float, default=0.0,
                     help="seconds after which a run that has not finished is aborted with an error line instead of "
                          "hanging the box (0 = 300 s + 2 s per step)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.scaling = "weak"
+    if args.global_batch > 0:
+        if args.global_batch % world:
+            ap.error(f"--global-batch {args.global_batch} is not a multiple of the {world} ranks")
+        args.batch, args.scaling = args.global_batch // world, "strong"
+    elif args.batch <= 0:
+        # BASELINE.json: configs[1] = 64 frames on one GPU, configs[2] = 512 frames sharded across 2 / 4 / 8 GPUs
+        args.batch = 64 if world == 1 else max(1, 512 // world)
+        args.scaling = "weak" if world == 1 else "strong"
+    return args
 
 
 def arm_stall_watchdog(args):
@@ -97,7 +114,33 @@ def load_peaks():
 
 def workload_name(args):
     a = {"vit_small": "ViT-S/8", "vit_base": "ViT-B/8"}[args.arch]
-    return f"{a} DINOSeg n_blocks={args.n_blocks}, {args.res}px, batch {args.batch} synthetic frames per GPU"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    shard = (f"batch {args.batch * world} synthetic frames sharded across {world} GPUs ({args.batch} per GPU)"
+             if world > 1 else f"batch {args.batch} synthetic frames on 1 GPU")
+    return f"{a} DINOSeg n_blocks={args.n_blocks}, {args.res}px, {shard}"
+
+
+def ncu_attention_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the attention kernel, from the newest committed
+    `ncu --set full` summary of the bench workload (profiles/r*_attn_ncu_full.csv, written by tools/ncu_summary.py)."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_attn_ncu_full.csv")), reverse=True):
+        try:
+            with open(path) as f:
+                rows = list(csv.DictReader(f))
+        except OSError:
+            continue
+        for r in rows:
+            if "attn_fwd_kernel" not in r.get("kernel", ""):
+                continue
+            try:
+                rd = float(next(v for k, v in r.items() if k.startswith("dram_read")))
+                wr = float(next(v for k, v in r.items() if k.startswith("dram_write")))
+            except (StopIteration, ValueError):
+                continue
+            return (rd + wr) * 1e6, os.path.relpath(path, ROOT), r.get("block", "")
+    return None, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -231,50 +274,64 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------
-def supervise(args):
-    """Single-GPU runs execute in a child process: if the child stalls (no result inside the stall limit) or dies on
-    a signal it is killed - which tears its CUDA context down - and the measurement is repeated ONCE.  The parent
-    prints the child's JSON line unchanged (plus `"attempt": 2` after a retry)."""
-    import ctypes
-    import subprocess
-    try:                                             # the supervising process maps the CUDA library as well (no torch
-        ctypes.CDLL(os.path.join(ROOT, "dino_b200", "lib", "libdinoseg.so"))   # import, no CUDA call): every process
-    except OSError:                                  # of a bench run shows the native code it is about to measure
-        pass
-    limit = args.stall_limit if args.stall_limit > 0 else 300.0 + 2.0 * (args.steps + args.warmup)
-    env = dict(os.environ, DINOSEG_BENCH_CHILD="1")
-    cmd = [sys.executable, os.path.abspath(__file__)] + sys.argv[1:]
-    why = "?"
-    for attempt in (1, 2):
-        try:
-            p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True, timeout=limit + 30.0)
-            rc, out = p.returncode, p.stdout
-        except subprocess.TimeoutExpired as e:
-            rc, out = 3, (e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or ""))
-        lines = [l for l in out.splitlines() if l.startswith("{")]
-        stalled = rc == 3 or rc < 0
-        if lines and not stalled:
-            line = lines[-1]
-            if attempt > 1:
-                d = json.loads(line)
-                d["attempt"] = attempt
-                line = json.dumps(d)
-            print(line, flush=True)
-            return rc
-        why = f"attempt {attempt}: exit code {rc}" + (" (stalled)" if stalled else "")
-        sys.stderr.write(f"bench.py: {why}; " + ("retrying once\n" if attempt == 1 and stalled else "giving up\n"))
-        if not stalled:
-            break
-    print(json.dumps({"error": f"bench run failed ({why})", "impl": args.impl}), flush=True)
-    return 3
+def extra_configs(args, dev, peaks):
+    """BASELINE.json configs[3] and configs[4] (per-GPU shape) on this GPU, in the same run: frames resident in HBM,
+    CUDA events around `steps` passes after 3 warm-ups, events around every attention launch, clocks sampled during the
+    timed region.  Parity of both shapes: tests/test_gpu_e2e.py::test_baseline_config_*."""
+    import torch
+    from dino_b200 import DINOSeg, synthetic
+    from dino_b200.flops import attention_flops_per_launch, flops_per_frame
+    peak_tf = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    res_out = {}
+    for key, arch, nb, res, batch in (("vit_s8_nb3_960px_b16", "vit_small", 3, 960, 16),
+                                      ("vit_b8_nb4_480px_b32", "vit_base", 4, 480, 32)):
+        cfg = synthetic.make_config(arch, nb, 7)
+        m = DINOSeg(head="mlp", n_blocks=nb, n_classes=7, arch=arch)
+        m.load_state_dict(synthetic.init_state_dict(cfg, 0, args.variant), strict=True)
+        m = m.to(dev)
+        m.set_resolution(res)
+        x = synthetic.make_frames(batch, res, seed=3).to(dev)
+        for _ in range(3):
+            m.infer(x, want_logprobs=False, want_labels=True)
+        torch.cuda.synchronize()
+        steps = max(3, min(args.steps, 10))
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        time.sleep(0.25)
+        m.profile_enable(True, kinds=("attention",))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            m.infer(x, want_logprobs=False, want_labels=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        sampler.stop()
+        ms = e0.elapsed_time(e1)
+        att_ms, att_n = m.profile_read().get("attention", (0.0, 0))
+        m.profile_enable(False)
+        g = res // 8
+        fl = attention_flops_per_launch(batch, g * g + 1, cfg["embed_dim"])
+        fps = batch * steps / (ms / 1e3)
+        step_tf = fps * flops_per_frame(cfg, res) / 1e12
+        a = {"workload": f"{ {'vit_small': 'ViT-S/8', 'vit_base': 'ViT-B/8'}[arch]} DINOSeg n_blocks={nb}, {res}px, batch {batch} "
+                         "synthetic frames on 1 GPU", "value": fps, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+             "whole_step_tflops": step_tf, "whole_step_frac_of_sustained_peak": step_tf / peak_tf,
+             "clocks": sampler.summary(t0, t1)}
+        if att_n:
+            ach = fl / (att_ms / att_n * 1e-3) / 1e12
+            a["attention"] = {"achieved_tflops": ach, "frac_of_sustained_peak": ach / peak_tf, "avg_launch_ms": att_ms / att_n,
+                              "tokens": g * g + 1, "heads": cfg["num_heads"], "share_of_step": att_ms / ms}
+        res_out[key] = a
+        del m, x
+        torch.cuda.empty_cache()
+    return res_out
 
 
 def main():
     args = parse_args()
-    if (args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) == 1
-            and os.environ.get("DINOSEG_BENCH_CHILD") != "1" and os.environ.get("DINOSEG_BENCH_NO_SUPERVISOR") != "1"):
-        return supervise(args)
-    arm_stall_watchdog(args)
+    arm_stall_watchdog(args)       # a run that does not finish ends with an error line and exit code 3; it is never retried
     if os.environ.get("DINOSEG_BENCH_TEST_STALL") == "1":     # test hook: behave like a run that never finishes
         time.sleep(1e9)
     if args.impl == "reference":
@@ -408,16 +465,21 @@ def main():
     N = g * g + 1
     f_launch = attention_flops_per_launch(B, N, cfg["embed_dim"])
     peak_tf = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    peak_burst = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
     roofline = None
     if att_n:
         ach = f_launch / (att_ms / att_n * 1e-3) / 1e12
+        traffic, traffic_src, traffic_block = (ncu_attention_traffic() if (B, res, args.arch) == (64, 480, "vit_small")
+                                               else (None, None, None))
         roofline = {"kernel": "attn_fwd_kernel (fused QK^T -> softmax -> PV, tcgen05/TMEM)", "bound": "tensor",
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
-                    # exact workload (profiles/r01_attn_ncu_full.csv): 531.1 MB + 158.0 MB; algorithmic = 531 MB of
-                    # q/k/v read once + 177 MB of output
-                    "traffic": 690.5e6 if (B, res, args.arch) == (64, 480, "vit_small") else None,
-                    "traffic_unit": "bytes per launch (ncu, profiles/r01_attn_ncu_full.csv)",
+                    # the kernel is timed inside a step that keeps the GPU under load, hence `peak` = the SUSTAINED cuBLAS
+                    # figure; the fraction of the burst figure (a kernel timed alone on a cool GPU) is given beside it
+                    "peak_burst": peak_burst, "frac_of_burst": ach / peak_burst,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, parsed from the committed ncu --set full
+                    # summary of this workload (algorithmic: 531 MB of q/k/v read once + 177 MB of output)
+                    "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                    "traffic_block_dim": traffic_block,
                     "peak_source": peaks_src + ", sustained figure (kernel timed inside a long step)",
                     "flops_per_launch": f_launch, "launches_timed": att_n, "avg_launch_ms": att_ms / att_n,
                     "share_of_step": att_ms / ms}
@@ -426,7 +488,7 @@ def main():
 
     out = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "weights": f"random init ({args.variant})",
                    "parallelism": f"replicas x{world} (frames sharded, no collective)", "host_cores_bound_per_rank": bound_cores,
@@ -435,10 +497,15 @@ def main():
                    "kernel_options": kernel_options(model)},
         "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline,
-        "whole_step": {"gflop_per_frame": F / 1e9, "achieved_tflops_per_gpu": step_tf, "frac_of_peak": step_tf / peak_tf},
+        "whole_step": {"gflop_per_frame": F / 1e9, "achieved_tflops_per_gpu": step_tf, "frac_of_peak": step_tf / peak_tf,
+                       "frac_of_burst": step_tf / peak_burst},
     }
     if kinds is not None:
         out["kernels"] = kinds
+    if world == 1 and not args.no_extra_configs and (args.arch, args.res, args.n_blocks) == ("vit_small", 480, 3):
+        del model, frames, labels                                  # free the workspace of the headline workload
+        torch.cuda.empty_cache()
+        out["extra_configs"] = extra_configs(args, dev, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # N = 1 only (bench contract)
         out["cpu_baseline"] = cpu_baseline(args, sd, cfg)
     if rank == 0:

@@ -15,9 +15,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdinoseg.so")
 SOURCES = [os.path.join(CSRC, "dinoseg_api.cu")]
-HEADERS = [
-    os.path.join(CSRC, f) for f in ("ptx.cuh", "gemm.cuh", "attention.cuh", "kernels.cuh")
-] + [os.path.join(os.path.dirname(HERE), "include", "dinoseg.h")]
+def headers() -> list:
+    """Everything the translation unit includes: every csrc/*.cuh plus the public header (globbed, so that a new
+    kernel header can never be forgotten by the staleness check)."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(HERE), "include", "dinoseg.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,7 +41,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in SOURCES + headers())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -25,8 +25,12 @@
 //                 (s_empty), long before P_t(j) exists: the softmax warps never wait for the tensor
 //                 pipe.  Issue order per key tile j:  QK0(j+1) QK1(j+1) PV0(j) PV1(j).
 //   warp 3      : idle (it only completes the producer warpgroup for setmaxnreg)
-//   warps 4..7  : softmax of query tile 0, one query row per thread (tcgen05.ld 32x32b)
-//   warps 8..11 : softmax of query tile 1
+//   softmax warps, SMW per query tile (template parameter):
+//     SMW = 4 (384 threads): warps 4..7 / 8..11, one query row per thread (tcgen05.ld 32x32b), 128 scores per thread
+//     SMW = 8 (640 threads): warps 4..11 / 12..19, each warp owns 16 rows and reads them in the 16x256b accumulator-
+//                 fragment layout: a row lives in one quad (32 of its 128 scores per thread, two rows per thread), the
+//                 row max is two quad shuffles.  Four softmax warps per scheduler instead of two: the tcgen05.ld /
+//                 row-max / barrier phases of one warp hide under the exponentials of the other three.
 // The exponentials are the bottleneck at head_dim 64 (16 MUFU.EX2 per clock per SM vs 8192 tensor
 // flop per clock; 2*128*128 exps per key tile = 2048 MUFU clocks vs 1354 clocks of MMA):
 //   * a quarter of the exponentials is evaluated with a degree-3 polynomial on the FMA/ALU pipes
@@ -60,7 +64,7 @@ struct AttnParams {
 constexpr int ATT_BM = 128;     // queries per tile (two tiles per work item)
 constexpr int ATT_BN = 128;     // keys per tile
 constexpr int ATT_DH = 64;      // head dim
-constexpr int ATT_THREADS = 384;
+constexpr int att_threads(int smw) { return 128 + 64 * smw; }   // producer warpgroup + 2 query tiles x SMW warps
 #ifndef DSG_ATTN_POLY_MASK
 #define DSG_ATTN_POLY_MASK 0x8888
 #endif
@@ -115,7 +119,6 @@ __host__ __device__ __forceinline__ AttItem att_decode(const AttnParams& p, int 
 
 // s_empty / p_full take one arrival per softmax THREAD: one arrival per warp (__syncwarp + elected lane) measured 6 %
 // slower for the whole kernel (1.60 vs 1.50 ms) - the extra convergence point costs more than the 124 arrivals.
-constexpr uint32_t ATT_ARRIVALS = 128;
 __device__ __forceinline__ void att_arrive(uint64_t* bar, int) { mbar_arrive(bar); }
 
 template <int KV_STAGES>
@@ -123,176 +126,35 @@ constexpr size_t attn_smem_bytes() {
   return size_t(2 + 2 * KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 }
 
-__device__ __forceinline__ void setmaxnreg_dec_80() { asm volatile("setmaxnreg.dec.sync.aligned.u32 80;"); }
-__device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
+template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
-template <int KV_STAGES>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t S_COL0 = 0;     // S_t: 128 fp32 columns at t*128
-  constexpr uint32_t P_COL0 = 256;   // P_t: 64 columns (128 bf16 keys, 2 per column) at 256 + t*64
-  constexpr uint32_t O_COL0 = 384;   // O_t: 64 fp32 columns at 384 + t*64
-  constexpr float LOG2E = 1.4426950408889634f;
-  constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays <= 2^8
+// TMEM columns (all 512): S_t 128 fp32 columns at t*128, P_t 64 columns (128 bf16 keys, two per column) at 256 + t*64,
+// O_t 64 fp32 columns at 384 + t*64
+constexpr uint32_t ATT_S_COL0 = 0, ATT_P_COL0 = 256, ATT_O_COL0 = 384;
+constexpr float ATT_LOG2E = 1.4426950408889634f;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays <= 2^8
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
-  uint8_t* smem = smem_raw + pad;
-  uint8_t* sQ = smem;                          // [2][16 KB]
-  uint8_t* sKV = smem + 2 * ATT_TILE_BYTES;    // [stage][K 16 KB | V 16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(2 + 2 * KV_STAGES) * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;                     // 1
-  uint64_t* q_empty = bars + 1;                // 1
-  uint64_t* kv_full = bars + 2;                // KV_STAGES
-  uint64_t* kv_empty = kv_full + KV_STAGES;    // KV_STAGES
-  uint64_t* s_full = kv_empty + KV_STAGES;     // 2: S_t(j) written by the tensor pipe
-  uint64_t* s_empty = s_full + 2;              // 2 (128 arrivals each): S_t(j) is in registers
-  uint64_t* p_full = s_empty + 2;              // 2 (128 arrivals each): P_t(j) written, O_t rescaled
-  uint64_t* pv_done = p_full + 2;              // 2: PV_t(j) retired (P_t free again, O_t stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+struct AttBars {
+  uint64_t *s_full, *s_empty, *p_full, *pv_done;
+};
 
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
-  const int lane = threadIdx.x & 31;
-  const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
+// 2^(s*log2e + nmb) for two scores: MUFU.EX2, or (a fixed share of the pairs) the polynomial on the FMA / ALU pipes
+__device__ __forceinline__ float2 att_exp_pair(float s0, float s1, float2 l2e, float2 nmb, bool poly) {
+  const float2 x = ffma2(make_float2(s0, s1), l2e, nmb);
+  return poly ? exp2_poly_x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+}
 
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 2);                       // one commit per MMA issuer
-    for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 2);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_empty[t], ATT_ARRIVALS);
-      mbar_init(&p_full[t], ATT_ARRIVALS);
-      mbar_init(&pv_done[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    setmaxnreg_dec_80();
-    if (warp == 0 && elect_one()) {
-      // ------------------------------ TMA producer ------------------------------
-      uint32_t kvc = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const AttItem I = att_decode(p, item);
-        const int h0 = I.bh[0] % p.H, b0 = I.bh[0] / p.H;
-        const int h1 = I.bh[1] % p.H, b1 = I.bh[1] / p.H;
-        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
-        mbar_expect_tx(q_full, I.act1 ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
-        tma_load_3d(sQ, &tmQKV, q_full, h0 * ATT_DH, I.q0[0], b0);
-        if (I.act1) tma_load_3d(sQ + ATT_TILE_BYTES, &tmQKV, q_full, h1 * ATT_DH, I.q0[1], b1);
-        const int streams = I.dual ? 2 : 1;
-        for (int j = 0; j < num_tiles; ++j) {
-          for (int u = 0; u < streams; ++u, ++kvc) {
-            const int h = u ? h1 : h0, b = u ? b1 : b0;
-            const int s = kvc % KV_STAGES;
-            mbar_wait(&kv_empty[s], ((kvc / KV_STAGES) & 1) ^ 1);
-            mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
-            uint8_t* sk = sKV + size_t(s) * 2 * ATT_TILE_BYTES;
-            tma_load_3d(sk, &tmQKV, &kv_full[s], p.D + h * ATT_DH, j * ATT_BN, b);
-            tma_load_3d(sk + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.D + h * ATT_DH, j * ATT_BN, b);
-          }
-        }
-      }
-    } else if ((warp == 1 || warp == 2) && elect_one()) {
-      // ------------------------------ MMA issuers ------------------------------
-      // one issuing thread per query tile (warp 1: tile 0, warp 2: tile 1): with a single in-order issuer the
-      // PV of one tile waits behind barrier waits that belong to the other tile
-      const int t = warp - 1;
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0);  // K^T: K-major B
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_DH, 1);  // V  : MN-major B
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + size_t(t) * ATT_TILE_BYTES));
-      const uint32_t s_tmem = tmem_base + S_COL0 + uint32_t(t * 128);
-      const uint32_t p_tmem = tmem_base + P_COL0 + uint32_t(t * 64);
-      const uint32_t o_tmem = tmem_base + O_COL0 + uint32_t(t * 64);
-      uint32_t kvc = 0, ct = 0;           // ct: key tiles of this query tile processed so far (barrier phases)
-      int it = 0;
-#ifdef DSG_ATTN_TIMING
-      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      long long tprev = clock64();
-#endif
-      auto issue_qk = [&](uint32_t kv_counter) {
-        const uint32_t sk = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES);
-        const uint64_t kdesc = umma_desc_sw128(sk);
-#pragma unroll
-        for (int k = 0; k < ATT_DH / 16; ++k)
-          umma_ss(s_tmem, qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk, k != 0);
-        tc_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](uint32_t kv_counter, bool accumulate) {
-        const uint32_t sv = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
-        const uint64_t vdesc = umma_desc_sw128(sv);
-        // P: 8 TMEM columns (16 bf16 keys) per K step; V: 16 keys = 2 KB per K step
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(o_tmem, p_tmem + uint32_t(k * 8), vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-        tc_commit(&pv_done[t]);
-      };
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const AttItem I = att_decode(p, item);
-        const bool active = t == 0 || I.act1;      // warpgroup 1 of an unpaired tail item has no tile
-        // ring position of this issuer's K/V tile j; in a dual item the other head's tiles sit in between
-        const uint32_t stride = I.dual ? 2u : 1u, off = I.dual ? uint32_t(t) : 0u;
-        auto own = [&](int j) { return kvc + uint32_t(j) * stride + off; };
-        mbar_wait(q_full, it & 1);
-        mbar_wait(&kv_full[own(0) % KV_STAGES], (own(0) / KV_STAGES) & 1);
-        tc_fence_after();
-        if (active) issue_qk(own(0));
-        if (num_tiles == 1) tc_commit(q_empty);
-        for (int j = 0; j < num_tiles; ++j) {
-          const bool more = j + 1 < num_tiles;
-          if (I.dual) {
-            // the other head's stage of this step is never read here: release it as soon as it has been filled (the
-            // wait keeps this arrival in the right phase of kv_empty)
-            const uint32_t o = kvc + uint32_t(j) * 2u + uint32_t(1 - t);
-            mbar_wait(&kv_full[o % KV_STAGES], (o / KV_STAGES) & 1);
-            mbar_arrive(&kv_empty[o % KV_STAGES]);
-          }
-          if (more) {
-            // next scores as soon as the softmax warps hold the current ones in registers
-            ATT_T(7);
-            mbar_wait(&kv_full[own(j + 1) % KV_STAGES], (own(j + 1) / KV_STAGES) & 1);
-            ATT_T(0);
-            if (active) {
-              mbar_wait(&s_empty[t], ct & 1);
-              ATT_T(1);
-              tc_fence_after();
-              issue_qk(own(j + 1));
-              ATT_T(6);
-            }
-            if (j + 2 == num_tiles) tc_commit(q_empty);  // this tile's last read of Q has been issued
-          }
-          if (active) {
-            ATT_T(7);
-            mbar_wait(&p_full[t], ct & 1); ++ct;
-            ATT_T(3);
-            tc_fence_after();
-            issue_pv(own(j), j != 0);
-            ATT_T(6);
-          }
-          tc_commit(&kv_empty[own(j) % KV_STAGES]);   // this tile's reads of K(j), V(j) have been issued
-        }
-        kvc += uint32_t(num_tiles) * stride;
-      }
-#ifdef DSG_ATTN_TIMING
-      if (p.timing != nullptr && t == 0)
-        for (int i = 0; i < 8; ++i) p.timing[(size_t(gridDim.x) * 2 + blockIdx.x) * 8 + i] = tacc[i];
-#endif
-    }
-  } else {
-    // ------------------------------ softmax warpgroups ------------------------------
-    setmaxnreg_inc_208();
+// ---------------------------------------------------------------------------------------------------------------
+// softmax, one query row per thread (SMW = 4: warps 4..7 query tile 0, 8..11 query tile 1)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void att_softmax_rows(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
+                                                 const int warp, const int lane, const int num_tiles) {
+  constexpr uint32_t S_COL0 = ATT_S_COL0, P_COL0 = ATT_P_COL0, O_COL0 = ATT_O_COL0;
+  constexpr float LOG2E = ATT_LOG2E, RESCALE_THRESHOLD = ATT_RESCALE_THRESHOLD;
+  uint64_t* const s_full = bars.s_full; uint64_t* const s_empty = bars.s_empty;
+  uint64_t* const p_full = bars.p_full; uint64_t* const pv_done = bars.pv_done;
+  {
     const int t = (warp - 4) >> 2;                 // query tile of this warpgroup
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
@@ -446,6 +308,322 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int i = 0; i < 8; ++i) p.timing[(size_t(blockIdx.x) * 2 + t) * 8 + i] = tacc[i];
     }
 #endif
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// softmax, 16 rows per warp in the accumulator-fragment layout (SMW = 8: warps 4..11 query tile 0, 12..19 tile 1).
+// Warp w serves TMEM lanes 32*(w%4) + 16*((w-4)/4 % 2) .. +15.  Thread (r = lane/4, q = lane%4) holds rows r and r+8 of
+// those 16 and, of every 8-key group k, the keys 8k + 2q, 8k + 2q + 1: 64 scores per key tile instead of 128, and
+// twice as many warps per scheduler to overlap the load / max / barrier phases with the exponentials.
+// The packed P words a thread produces (row r or r+8, keys 8k+2q, 8k+2q+1 -> P column 4k+q) are exactly its
+// registers of a tcgen05.st 16x128b.x16.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
+                                                  const int warp, const int lane, const int num_tiles) {
+  constexpr float LOG2E = ATT_LOG2E;
+  const int t = (warp - 4) >> 3;                   // query tile of this warp
+  const int rbase = (warp & 3) * 32 + (((warp - 4) >> 2) & 1) * 16;   // first of the warp's 16 rows (= TMEM lanes)
+  const int qd = lane & 3, r8 = lane >> 2;
+  const uint32_t lane_base = tmem_base + (uint32_t(rbase) << 16);
+  const uint32_t s_addr = lane_base + ATT_S_COL0 + uint32_t(t * 128);
+  const uint32_t p_addr = lane_base + ATT_P_COL0 + uint32_t(t * 64);
+  const uint32_t o_addr = lane_base + ATT_O_COL0 + uint32_t(t * 64);
+  const float2 l2e = make_float2(LOG2E, LOG2E);
+  uint32_t sc = 0;                                 // key tiles processed so far by this query tile
+
+  for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    const AttItem I = att_decode(p, item);
+    if (t == 1 && !I.act1) continue;               // unpaired tail item
+    const int bh = t ? I.bh[1] : I.bh[0];
+    const int h = bh % p.H, b = bh / p.H;
+    const int q0 = t ? I.q0[1] : I.q0[0];
+    float m0 = 0.f, m1 = 0.f;                      // (stale) running maxima of rows r8 and r8 + 8 (raw scores)
+    float l0 = 0.f, l1 = 0.f;                      // this thread's share of the running row sums of exp(s - m)
+
+    for (int j = 0; j < num_tiles; ++j, ++sc) {
+      mbar_wait(&bars.s_full[t], sc & 1);
+      tc_fence_after();
+      uint32_t sr[64];
+      tmem_ld_16x256b_x16(s_addr, sr);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars.s_empty[t]);               // the tensor pipe may overwrite S_t with the next scores
+      const int kbase = j * ATT_BN;
+      if (kbase + ATT_BN > p.N) {                  // last key tile of a ragged sequence: keys >= N do not exist
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int key = kbase + 8 * k + 2 * qd;
+          if (key >= p.N) sr[4 * k] = sr[4 * k + 2] = 0xff800000u;          // -inf
+          if (key + 1 >= p.N) sr[4 * k + 1] = sr[4 * k + 3] = 0xff800000u;
+        }
+      }
+      auto S = [&](int i) { return __uint_as_float(sr[i]); };
+      float mx0 = fmaxf(S(0), S(1)), mx1 = fmaxf(S(2), S(3));
+#pragma unroll
+      for (int k = 1; k < 16; ++k) {
+        mx0 = fmaxf(mx0, fmaxf(S(4 * k), S(4 * k + 1)));
+        mx1 = fmaxf(mx1, fmaxf(S(4 * k + 2), S(4 * k + 3)));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      // lazy rescale: the reference maximum of a row only moves when the row max has grown by more than 2^8
+      const bool g0 = j == 0 || (mx0 - m0) * LOG2E > ATT_RESCALE_THRESHOLD;
+      const bool g1 = j == 0 || (mx1 - m1) * LOG2E > ATT_RESCALE_THRESHOLD;
+      const float n0 = g0 ? mx0 : m0, n1 = g1 ? mx1 : m1;
+      const float2 nmb0 = make_float2(-n0 * LOG2E, -n0 * LOG2E), nmb1 = make_float2(-n1 * LOG2E, -n1 * LOG2E);
+      float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
+      uint32_t pk[32];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 e0 = att_exp_pair(S(4 * k), S(4 * k + 1), l2e, nmb0, (ATT_POLY_MASK >> ((2 * k) & 15)) & 1);
+        const float2 e1 = att_exp_pair(S(4 * k + 2), S(4 * k + 3), l2e, nmb1, (ATT_POLY_MASK >> ((2 * k + 1) & 15)) & 1);
+        sum0 = fadd2(sum0, e0);
+        sum1 = fadd2(sum1, e1);
+        pk[2 * k] = pack_bf16x2(e0.x, e0.y);
+        pk[2 * k + 1] = pack_bf16x2(e1.x, e1.y);
+      }
+      if (j > 0) {
+        // PV_t(j-1) must have retired before P_t is overwritten or O_t is rescaled
+        mbar_wait(&bars.pv_done[t], (sc - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, g0 || g1)) {
+          const float a0 = fast_exp2((m0 - n0) * LOG2E), a1 = fast_exp2((m1 - n1) * LOG2E);   // 1 for rows that keep m
+          uint32_t o[32];
+          tmem_ld_16x256b_x8(o_addr, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            o[4 * k] = __float_as_uint(__uint_as_float(o[4 * k]) * a0);
+            o[4 * k + 1] = __float_as_uint(__uint_as_float(o[4 * k + 1]) * a0);
+            o[4 * k + 2] = __float_as_uint(__uint_as_float(o[4 * k + 2]) * a1);
+            o[4 * k + 3] = __float_as_uint(__uint_as_float(o[4 * k + 3]) * a1);
+          }
+          tmem_st_16x256b_x8(o_addr, o);
+          l0 *= a0;
+          l1 *= a1;
+        }
+      }
+      m0 = n0;
+      m1 = n1;
+      l0 += sum0.x + sum0.y;
+      l1 += sum1.x + sum1.y;
+      tmem_st_16x128b_x16(p_addr, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars.p_full[t]);
+    }
+
+    // epilogue: O / l -> bf16 -> out[b*N + q, h*64 + d].  Row sums: add the quad's four shares; the O rows are read
+    // as 16x32bx2 (lane i and i+16: row i % 16, columns 0..31 / 32..63), so each thread stores 64 contiguous bytes
+    mbar_wait(&bars.pv_done[t], (sc - 1) & 1);
+    tc_fence_after();
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const int r = lane & 15, ch = lane >> 4;
+    const float la = __shfl_sync(0xffffffffu, l0, 4 * (r & 7)), lb = __shfl_sync(0xffffffffu, l1, 4 * (r & 7));
+    const float inv_l = 1.0f / (r < 8 ? la : lb);
+    uint32_t o[32];
+    tmem_ld_16x32bx2_x32(o_addr, o);
+    tmem_ld_wait();
+    const int q = q0 + rbase + r;
+    if (q < p.N) {
+      __nv_bfloat16* dst = p.out + (size_t(b) * p.N + q) * p.D + h * ATT_DH + ch * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+        v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + i) = v;
+      }
+    }
+    __syncwarp();
+    // O_t is free again once every thread's tcgen05.ld has completed (wait::ld above); the next item's first PV_t is
+    // ordered after this query tile's next p_full arrivals.
+    tc_fence_before();
+  }
+}
+
+template <int KV_STAGES, int SMW>
+__global__ void __launch_bounds__(att_threads(SMW), 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  static_assert(SMW == 4 || SMW == 8, "softmax warps per query tile");
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t S_COL0 = ATT_S_COL0, P_COL0 = ATT_P_COL0, O_COL0 = ATT_O_COL0;
+  constexpr uint32_t ATT_ARRIVALS = 32 * SMW;    // s_empty / p_full: one arrival per softmax thread of the query tile
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sQ = smem;                          // [2][16 KB]
+  uint8_t* sKV = smem + 2 * ATT_TILE_BYTES;    // [stage][K 16 KB | V 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(2 + 2 * KV_STAGES) * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* q_empty = bars + 1;                // 1
+  uint64_t* kv_full = bars + 2;                // KV_STAGES
+  uint64_t* kv_empty = kv_full + KV_STAGES;    // KV_STAGES
+  uint64_t* s_full = kv_empty + KV_STAGES;     // 2: S_t(j) written by the tensor pipe
+  uint64_t* s_empty = s_full + 2;              // 2 (ATT_ARRIVALS each): S_t(j) is in registers
+  uint64_t* p_full = s_empty + 2;              // 2 (ATT_ARRIVALS each): P_t(j) written, O_t rescaled
+  uint64_t* pv_done = p_full + 2;              // 2: PV_t(j) retired (P_t free again, O_t stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);                       // one commit per MMA issuer
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 2);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], ATT_ARRIVALS);
+      mbar_init(&p_full[t], ATT_ARRIVALS);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // registers move from the producer warpgroup to the softmax warps: 128*80 + 256*208 (SMW = 4) and
+    // 128*56 + 512*112 (SMW = 8) both fit the 64 K registers of an SM
+    if constexpr (SMW == 4) setmaxnreg_dec<80>(); else setmaxnreg_dec<56>();
+    if (warp == 0 && elect_one()) {
+      // ------------------------------ TMA producer ------------------------------
+      uint32_t kvc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const AttItem I = att_decode(p, item);
+        const int h0 = I.bh[0] % p.H, b0 = I.bh[0] / p.H;
+        const int h1 = I.bh[1] % p.H, b1 = I.bh[1] / p.H;
+        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
+        mbar_expect_tx(q_full, I.act1 ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
+        tma_load_3d(sQ, &tmQKV, q_full, h0 * ATT_DH, I.q0[0], b0);
+        if (I.act1) tma_load_3d(sQ + ATT_TILE_BYTES, &tmQKV, q_full, h1 * ATT_DH, I.q0[1], b1);
+        const int streams = I.dual ? 2 : 1;
+        for (int j = 0; j < num_tiles; ++j) {
+          for (int u = 0; u < streams; ++u, ++kvc) {
+            const int h = u ? h1 : h0, b = u ? b1 : b0;
+            const int s = kvc % KV_STAGES;
+            mbar_wait(&kv_empty[s], ((kvc / KV_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
+            uint8_t* sk = sKV + size_t(s) * 2 * ATT_TILE_BYTES;
+            tma_load_3d(sk, &tmQKV, &kv_full[s], p.D + h * ATT_DH, j * ATT_BN, b);
+            tma_load_3d(sk + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.D + h * ATT_DH, j * ATT_BN, b);
+          }
+        }
+      }
+    } else if ((warp == 1 || warp == 2) && elect_one()) {
+      // ------------------------------ MMA issuers ------------------------------
+      // one issuing thread per query tile (warp 1: tile 0, warp 2: tile 1): with a single in-order issuer the
+      // PV of one tile waits behind barrier waits that belong to the other tile
+      const int t = warp - 1;
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0);  // K^T: K-major B
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_DH, 1);  // V  : MN-major B
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + size_t(t) * ATT_TILE_BYTES));
+      const uint32_t s_tmem = tmem_base + S_COL0 + uint32_t(t * 128);
+      const uint32_t p_tmem = tmem_base + P_COL0 + uint32_t(t * 64);
+      const uint32_t o_tmem = tmem_base + O_COL0 + uint32_t(t * 64);
+      uint32_t kvc = 0, ct = 0;           // ct: key tiles of this query tile processed so far (barrier phases)
+      int it = 0;
+#ifdef DSG_ATTN_TIMING
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tprev = clock64();
+#endif
+      auto issue_qk = [&](uint32_t kv_counter) {
+        const uint32_t sk = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES);
+        const uint64_t kdesc = umma_desc_sw128(sk);
+#pragma unroll
+        for (int k = 0; k < ATT_DH / 16; ++k)
+          umma_ss(s_tmem, qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk, k != 0);
+        tc_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](uint32_t kv_counter, bool accumulate) {
+        const uint32_t sv = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
+        const uint64_t vdesc = umma_desc_sw128(sv);
+        // P: 8 TMEM columns (16 bf16 keys) per K step; V: 16 keys = 2 KB per K step
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_ts(o_tmem, p_tmem + uint32_t(k * 8), vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+        tc_commit(&pv_done[t]);
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const AttItem I = att_decode(p, item);
+        const bool active = t == 0 || I.act1;      // warpgroup 1 of an unpaired tail item has no tile
+        // ring position of this issuer's K/V tile j; in a dual item the other head's tiles sit in between
+        const uint32_t stride = I.dual ? 2u : 1u, off = I.dual ? uint32_t(t) : 0u;
+        auto own = [&](int j) { return kvc + uint32_t(j) * stride + off; };
+        mbar_wait(q_full, it & 1);
+        mbar_wait(&kv_full[own(0) % KV_STAGES], (own(0) / KV_STAGES) & 1);
+        tc_fence_after();
+        if (active) issue_qk(own(0));
+        if (num_tiles == 1) tc_commit(q_empty);
+        for (int j = 0; j < num_tiles; ++j) {
+          const bool more = j + 1 < num_tiles;
+          if (I.dual) {
+            // the other head's stage of this step is never read here: release it as soon as it has been filled (the
+            // wait keeps this arrival in the right phase of kv_empty)
+            const uint32_t o = kvc + uint32_t(j) * 2u + uint32_t(1 - t);
+            mbar_wait(&kv_full[o % KV_STAGES], (o / KV_STAGES) & 1);
+            mbar_arrive(&kv_empty[o % KV_STAGES]);
+          }
+          if (more) {
+            // next scores as soon as the softmax warps hold the current ones in registers
+            ATT_T(7);
+            mbar_wait(&kv_full[own(j + 1) % KV_STAGES], (own(j + 1) / KV_STAGES) & 1);
+            ATT_T(0);
+            if (active) {
+              mbar_wait(&s_empty[t], ct & 1);
+              ATT_T(1);
+              tc_fence_after();
+              issue_qk(own(j + 1));
+              ATT_T(6);
+            }
+            if (j + 2 == num_tiles) tc_commit(q_empty);  // this tile's last read of Q has been issued
+          }
+          if (active) {
+            ATT_T(7);
+            mbar_wait(&p_full[t], ct & 1); ++ct;
+            ATT_T(3);
+            tc_fence_after();
+            issue_pv(own(j), j != 0);
+            ATT_T(6);
+          }
+          tc_commit(&kv_empty[own(j) % KV_STAGES]);   // this tile's reads of K(j), V(j) have been issued
+        }
+        kvc += uint32_t(num_tiles) * stride;
+      }
+#ifdef DSG_ATTN_TIMING
+      if (p.timing != nullptr && t == 0)
+        for (int i = 0; i < 8; ++i) p.timing[(size_t(gridDim.x) * 2 + blockIdx.x) * 8 + i] = tacc[i];
+#endif
+    }
+  } else {
+    // ------------------------------ softmax warps ------------------------------
+    const AttBars ab{s_full, s_empty, p_full, pv_done};
+    if constexpr (SMW == 4) {
+      setmaxnreg_inc<208>();
+      att_softmax_rows(p, tmem_base, ab, warp, lane, num_tiles);
+    } else {
+      setmaxnreg_inc<112>();
+      att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
+    }
   }
 
   tc_fence_before();

@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -281,9 +282,19 @@ void attn_plan_items(AttnParams& p) {
   p.num_items = p.B * p.H * p.full_pairs + (p.lone ? (p.B * p.H + 1) / 2 : 0);
 }
 
-cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
-  p.timing = g_attn_timing;
-  auto kern = attn_fwd_kernel<kAttnStages>;
+// softmax warps per query tile: 8 (16-row warps in the accumulator-fragment layout, 640 threads) or 4 (one row per
+// thread, 384 threads); DINOSEG_ATTN_SMW overrides for A/B measurements
+int attn_smw() {
+  static const int v = [] {
+    const char* e = getenv("DINOSEG_ATTN_SMW");
+    return (e && atoi(e) == 4) ? 4 : 8;
+  }();
+  return v;
+}
+
+template <int SMW>
+cudaError_t launch_attention_t(const CUtensorMap& qkv, const AttnParams& p, int num_sms, cudaStream_t s) {
+  auto kern = attn_fwd_kernel<kAttnStages, SMW>;
   constexpr size_t smem = attn_smem_bytes<kAttnStages>();
   static bool attr[64] = {};
   int dev = 0;
@@ -293,10 +304,15 @@ cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, 
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  attn_plan_items(p);
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
-  kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
+  kern<<<grid, att_threads(SMW), smem, s>>>(qkv, p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
+  p.timing = g_attn_timing;
+  attn_plan_items(p);
+  return attn_smw() == 8 ? launch_attention_t<8>(qkv, p, num_sms, s) : launch_attention_t<4>(qkv, p, num_sms, s);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int M, int D, float eps,
@@ -384,8 +400,19 @@ struct WorkBufs {
 // Worker threads of the host entry points (label-map expansion, see predict_host_impl).
 class HostPool {
  public:
-  explicit HostPool(int n) {
-    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { run(); });
+  // `spawn` exists for the unit test (dinoseg_debug_host_pool): it lets a thread creation fail on purpose.
+  explicit HostPool(int n, const std::function<void(int)>& spawn_hook = nullptr) {
+    try {
+      for (int i = 0; i < n; ++i) {
+        if (spawn_hook) spawn_hook(i);
+        threads_.emplace_back([this] { run(); });
+      }
+    } catch (...) {
+      // std::thread could not be created (EAGAIN: pids / nproc limit).  A smaller pool still does the job; with no
+      // thread at all the caller falls back to the DMA path.  Never unwind with joinable threads in threads_
+      // (std::terminate) or with workers that hold a dangling `this`.
+      if (threads_.empty()) throw;
+    }
   }
   ~HostPool() {
     { std::lock_guard<std::mutex> g(m_); stop_ = true; }
@@ -556,7 +583,7 @@ WsLayout ws_layout(const dinoseg* h, int batch) {
   L.abuf = off; off = align_up(off + M * D * 2, 1024);
   L.qkv = off; off = align_up(off + M * 3 * D * 2, 1024);
   size_t hid_bytes = M * size_t(h->cfg.mlp_hidden) * 2;
-  const size_t h1_bytes = M * size_t(h->cfg.head_h1) * 4;
+  const size_t h1_bytes = M * size_t(2 * kHeadPart) * 2;   // relu(layer_1) as bf16x3 [M, hi | lo], kHeadPart columns each
   const size_t im2col_bytes = size_t(batch) * h->P * IM2COL_KA * 2;
   if (h1_bytes > hid_bytes) hid_bytes = h1_bytes;
   if (im2col_bytes > hid_bytes) hid_bytes = im2col_bytes;
@@ -1030,6 +1057,10 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
   // bf16 rounding would otherwise be the largest contribution to the log-prob error.
   { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, h->norm_g, h->norm_b, w.qkv, M, D, eps, true, s)); ++n; }
   uint8_t* lr = lowres ? lowres : w.lowres;
+  // tail kernel: eight lanes per patch, 32 patches per 256-thread block; it also writes the p x p blocks of the int64
+  // label map (reference pl_torch_modules.py:297-298) when the caller wants one and the map is not empty (p = 480 // g)
+  const int tail_grid = std::min((batch * h->P + 31) / 32, 16 * h->num_sms);
+  long long* tail_labels = (labels && h->p_rep > 0) ? reinterpret_cast<long long*>(labels) : nullptr;
   if (h->cfg.head_kind == 1) {
     // 'linear' head (pl_torch_modules.py:127-138): one bf16x3 GEMM -> logits [M, C] (row pitch kLinPitch) -> log_softmax
     {
@@ -1038,10 +1069,9 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       LaunchScope ls(h, K_GEMM_HEAD, s);
       DSG_CUDA(h, launch_gemm(EPI_BIAS_F32, w.tm_qkv_a, h->tm_h1, w.tm_lin_out, w.tm_lin_out, p, sms, s)); ++n;
     }
-    const int rows = batch * h->P;
     LaunchScope ls(h, K_HEAD_TAIL, s);
-    linear_tail_kernel<<<(rows + 255) / 256, 256, 0, s>>>(w.x, kLinPitch, logprobs, lr, batch, h->P, h->Ntok,
-                                                          h->cfg.n_classes);
+    head_tail_kernel<true><<<tail_grid, 256, 0, s>>>(w.x, kLinPitch, nullptr, nullptr, logprobs, lr, tail_labels, batch,
+                                                     h->g, h->p_rep, h->Ntok, 0, h->cfg.n_classes);
     DSG_CUDA(h, cudaGetLastError()); ++n;
   } else {
     {
@@ -1057,14 +1087,11 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       LaunchScope ls(h, K_GEMM_HEAD, s);
       DSG_CUDA(h, launch_gemm(EPI_RELU_F32, w.tm_h1s_a, h->tm_h2, w.tm_h2_out, w.tm_h2_out, p, sms, s)); ++n;
     }
-    const int rows = batch * h->P;
-    const int grid = (rows + 255) / 256;
     LaunchScope ls(h, K_HEAD_TAIL, s);
-    head_tail_kernel<<<grid, 256, 0, s>>>(w.x, h->w3, h->b3, logprobs, lr, batch, h->P, h->Ntok, h->cfg.head_h2,
-                                          h->cfg.n_classes);
+    head_tail_kernel<false><<<tail_grid, 256, 0, s>>>(w.x, h->cfg.head_h2, h->w3, h->b3, logprobs, lr, tail_labels, batch,
+                                                      h->g, h->p_rep, h->Ntok, h->cfg.head_h2, h->cfg.n_classes);
     DSG_CUDA(h, cudaGetLastError()); ++n;
   }
-  if (labels) { LaunchScope ls(h, K_REPLICATE, s); DSG_CUDA(h, launch_replicate(lr, labels, batch, h->g, h->p_rep, s)); ++n; }
   h->launches = n;
   return 0;
 }

@@ -282,10 +282,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           GEMM_T(2);
         }
       }
-#ifdef DSG_PAIR_TAIL
-      // Producer tail (NOT yet validated on hardware, hence opt-in at compile time): the
-      // leader's last multicast commits on this CTA's stage-empty barriers are otherwise never waited for, and the
-      // CTA must not exit while one of them may still be in flight towards its shared memory.
+      // Producer tail: the leader's last multicast commits on this CTA's stage-empty barriers are otherwise never waited
+      // for, and a CTA must not exit while an arrival may still be in flight towards its shared memory (it would land
+      // in whatever the next CTA on this SM keeps there).
       if constexpr (PAIR) {
         for (uint32_t i = 0; i < uint32_t(STAGES) && i < kc; ++i) {
           const uint32_t idx = kc - 1 - i;
@@ -298,7 +297,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-#endif
       GEMM_T_DUMP(0);
     }
   } else if (warp == 1) {

@@ -303,60 +303,96 @@ half_counts_kernel(const uint8_t* __restrict__ lowres, int32_t* __restrict__ cou
 // argmax with torch semantics: first maximum wins, NaN counts as the maximum
 // (reference pl_torch_modules.py:295 torch.argmax)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int argmax_first(const float* v, int C) {
+constexpr int HEAD_MAX_C = 16;
+
+// v has HEAD_MAX_C entries (C valid); fully unrolled so that v stays in registers
+__device__ __forceinline__ int argmax_first(const float (&v)[HEAD_MAX_C], int C) {
   float best = v[0];
   int idx = 0;
-  for (int c = 1; c < C; ++c) {
+#pragma unroll
+  for (int c = 1; c < HEAD_MAX_C; ++c) {
     const float x = v[c];
-    if ((x > best) || (x != x && best == best)) { best = x; idx = c; }
+    if (c < C && ((x > best) || (x != x && best == best))) { best = x; idx = c; }
   }
   return idx;
 }
 
-constexpr int HEAD_MAX_C = 16;
 
 // ---------------------------------------------------------------------------------------
-// Head tail: h2 (= relu(layer_2(relu(layer_1))), fp32, produced by the two tensor-core GEMMs) ->
-// layer_3 -> log_softmax -> argmax   (reference pl_torch_modules.py:121-123, :295), fp32 CUDA cores.
+// Head tail: layer_3 -> log_softmax -> argmax -> p x p replication   (reference pl_torch_modules.py:121-123 / :135-138,
+// :295, :297-298 np.kron), fp32 CUDA cores, HBM-bound (reads 400 B per patch, writes 8*p*p B per patch).
+//   LINEAR = false: in = h2 = relu(layer_2(relu(layer_1))) [B*Ntok, ld] fp32 (produced by the two tensor-core GEMMs),
+//                   z = in . W3^T + b3;   LINEAR = true: in = the 'linear' head's logits [B*Ntok, ld], z = in[:C].
 // Input rows are tokens INCLUDING the cls row of every frame; output rows drop it (reference :243).
-// One thread per patch row; W3 / b3 live in shared memory.
+// Eight lanes per patch row (four rows per warp per step): the lanes read the row as consecutive float4 (coalesced),
+// keep partial dot products for all classes, all-reduce them with three xor-shuffles, and then every lane holds the
+// row's logits.  The label is written to the low-res map and - fused, labels != nullptr - replicated into its p x p
+// block of the int64 map: the eight lanes take the block's rows, 16-byte stores when p is even (the four patches of
+// a warp are neighbours, so every output row receives 4*p*8 contiguous bytes per step).
 // ---------------------------------------------------------------------------------------
 constexpr int HT_MAX_H2 = 104;
 
+template <bool LINEAR>
 __global__ void __launch_bounds__(256)
-head_tail_kernel(const float* __restrict__ h2 /*[B*Ntok, H2]*/, const float* __restrict__ w3 /*[C, H2]*/,
+head_tail_kernel(const float* __restrict__ in /*[B*Ntok, ld]*/, int ld, const float* __restrict__ w3 /*[C, H2]*/,
                  const float* __restrict__ b3 /*[C]*/, float* __restrict__ logprobs /*[B*P, C] or null*/,
-                 uint8_t* __restrict__ lowres /*[B*P] or null*/, int B, int P, int Ntok, int H2, int C) {
-  __shared__ float sW3[HEAD_MAX_C * HT_MAX_H2];
+                 uint8_t* __restrict__ lowres /*[B*P] or null*/, long long* __restrict__ labels /*[B, g*p, g*p] or null*/,
+                 int B, int g, int p, int Ntok, int H2, int C) {
+  __shared__ float sW3[LINEAR ? 1 : HEAD_MAX_C * HT_MAX_H2];
   __shared__ float sB3[HEAD_MAX_C];
-  for (int i = threadIdx.x; i < HEAD_MAX_C * HT_MAX_H2; i += blockDim.x) {
-    const int c = i / HT_MAX_H2, k = i - c * HT_MAX_H2;
-    sW3[i] = (c < C && k < H2) ? w3[c * H2 + k] : 0.f;
+  if constexpr (!LINEAR) {
+    for (int i = threadIdx.x; i < HEAD_MAX_C * HT_MAX_H2; i += blockDim.x) {
+      const int c = i / HT_MAX_H2, k = i - c * HT_MAX_H2;
+      sW3[i] = (c < C && k < H2) ? w3[c * H2 + k] : 0.f;
+    }
+    if (threadIdx.x < HEAD_MAX_C) sB3[threadIdx.x] = threadIdx.x < C ? b3[threadIdx.x] : 0.f;
+    __syncthreads();
   }
-  if (threadIdx.x < HEAD_MAX_C) sB3[threadIdx.x] = threadIdx.x < C ? b3[threadIdx.x] : 0.f;
-  __syncthreads();
+  const int P = g * g;
   const int total_rows = B * P;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_rows; r += gridDim.x * blockDim.x) {
-    const int b = r / P, t = r - b * P;
-    const float4* src = reinterpret_cast<const float4*>(h2 + (size_t(b) * Ntok + 1 + t) * H2);
+  const int sub = threadIdx.x & 7;                           // lane within the row's group of eight
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int ngrp = (gridDim.x * blockDim.x) >> 3;
+  const int W = g * p;
+  for (int r0 = 0; r0 < total_rows; r0 += ngrp) {            // uniform trip count: the shuffles below need full warps
+    const int r = r0 + grp;
+    const bool live = r < total_rows;
+    const int rr = live ? r : total_rows - 1;
+    const int b = rr / P, t = rr - b * P;
+    const float* src = in + (size_t(b) * Ntok + 1 + t) * ld;
     float z[HEAD_MAX_C];
 #pragma unroll
     for (int c = 0; c < HEAD_MAX_C; ++c) z[c] = 0.f;
-    for (int k4 = 0; k4 < H2 / 4; ++k4) {
-      const float4 hv = __ldg(src + k4);
+    if constexpr (LINEAR) {
+#pragma unroll
+      for (int c = 0; c < HEAD_MAX_C; ++c)
+        if (c < C) z[c] = __ldg(src + c);
+    } else {
+      for (int k4 = sub; k4 < H2 / 4; k4 += 8) {
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(src) + k4);
+#pragma unroll
+        for (int c = 0; c < HEAD_MAX_C; ++c) {
+          if (c < C) {
+            const float* wr = sW3 + c * HT_MAX_H2 + 4 * k4;
+            z[c] = fmaf(hv.x, wr[0], z[c]); z[c] = fmaf(hv.y, wr[1], z[c]);
+            z[c] = fmaf(hv.z, wr[2], z[c]); z[c] = fmaf(hv.w, wr[3], z[c]);
+          }
+        }
+      }
 #pragma unroll
       for (int c = 0; c < HEAD_MAX_C; ++c) {
         if (c < C) {
-          const float* wr = sW3 + c * HT_MAX_H2 + 4 * k4;
-          z[c] = fmaf(hv.x, wr[0], z[c]); z[c] = fmaf(hv.y, wr[1], z[c]);
-          z[c] = fmaf(hv.z, wr[2], z[c]); z[c] = fmaf(hv.w, wr[3], z[c]);
+          z[c] += __shfl_xor_sync(0xffffffffu, z[c], 1);
+          z[c] += __shfl_xor_sync(0xffffffffu, z[c], 2);
+          z[c] += __shfl_xor_sync(0xffffffffu, z[c], 4);
+          z[c] += sB3[c];
         }
       }
     }
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < HEAD_MAX_C; ++c)
-      if (c < C) { z[c] += sB3[c]; mx = fmaxf(mx, z[c]); }
+      if (c < C) mx = fmaxf(mx, z[c]);
     float se = 0.f;
 #pragma unroll
     for (int c = 0; c < HEAD_MAX_C; ++c)
@@ -365,43 +401,30 @@ head_tail_kernel(const float* __restrict__ h2 /*[B*Ntok, H2]*/, const float* __r
 #pragma unroll
     for (int c = 0; c < HEAD_MAX_C; ++c)
       if (c < C) z[c] = (z[c] - mx) - lse;
+    if (!live) continue;
     if (logprobs != nullptr) {
 #pragma unroll
       for (int c = 0; c < HEAD_MAX_C; ++c)
-        if (c < C) logprobs[size_t(r) * C + c] = z[c];
+        if (c < C && (c & 7) == sub) logprobs[size_t(r) * C + c] = z[c];
     }
-    if (lowres != nullptr) lowres[r] = uint8_t(argmax_first(z, C));
-  }
-}
-
-// 'linear' head tail (reference pl_torch_modules.py:135-138): logits z [B*Ntok, ldz] (cls rows included, C valid
-// columns) -> log_softmax -> argmax.  One thread per patch row.
-__global__ void __launch_bounds__(256)
-linear_tail_kernel(const float* __restrict__ z, int ldz, float* __restrict__ logprobs, uint8_t* __restrict__ lowres,
-                   int B, int P, int Ntok, int C) {
-  const int total_rows = B * P;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total_rows; r += gridDim.x * blockDim.x) {
-    const int b = r / P, t = r - b * P;
-    const float* src = z + (size_t(b) * Ntok + 1 + t) * ldz;
-    float v[HEAD_MAX_C];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c)
-      if (c < C) { v[c] = src[c]; mx = fmaxf(mx, v[c]); }
-    float se = 0.f;
-#pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c)
-      if (c < C) se += expf(v[c] - mx);
-    const float lse = logf(se);
-#pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c)
-      if (c < C) v[c] = (v[c] - mx) - lse;
-    if (logprobs != nullptr) {
-#pragma unroll
-      for (int c = 0; c < HEAD_MAX_C; ++c)
-        if (c < C) logprobs[size_t(r) * C + c] = v[c];
+    const int label = argmax_first(z, C);
+    if (lowres != nullptr && sub == 0) lowres[r] = uint8_t(label);
+    if (labels != nullptr) {
+      const int i = t / g, j = t - i * g;
+      long long* blk = labels + (size_t(b) * W + size_t(i) * p) * W + size_t(j) * p;
+      if ((p & 1) == 0) {
+        const longlong2 v = make_longlong2(label, label);
+        for (int yy = sub; yy < p; yy += 8) {
+          longlong2* row = reinterpret_cast<longlong2*>(blk + size_t(yy) * W);
+          for (int x2 = 0; x2 < (p >> 1); ++x2) row[x2] = v;
+        }
+      } else {
+        for (int yy = sub; yy < p; yy += 8) {
+          long long* row = blk + size_t(yy) * W;
+          for (int x = 0; x < p; ++x) row[x] = label;
+        }
+      }
     }
-    if (lowres != nullptr) lowres[r] = uint8_t(argmax_first(v, C));
   }
 }
 
@@ -411,7 +434,8 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logprobs, uint8_t* 
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float z[HEAD_MAX_C];
-  for (int c = 0; c < C; ++c) z[c] = logprobs[size_t(r) * C + c];
+#pragma unroll
+  for (int c = 0; c < HEAD_MAX_C; ++c) z[c] = c < C ? logprobs[size_t(r) * C + c] : 0.f;
   lowres[r] = uint8_t(argmax_first(z, C));
 }
 

@@ -238,9 +238,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (i >= MLP_LAG) load_w2(i - MLP_LAG);
         }
       }
-#ifdef DSG_PAIR_TAIL
-      // Producer tail (NOT yet validated on hardware, hence opt-in at compile time): wait
-      // for the leader's last multicast commits on this CTA's w_empty / a_empty barriers before the CTA may exit.
+      // Producer tail: wait for the leader's last multicast commits on this CTA's w_empty / a_empty barriers before the
+      // CTA may exit (an arrival still in flight would land in the shared memory of the next CTA on this SM).
       if constexpr (PAIR) {
         for (uint32_t i = 0; i < uint32_t(RING) && i < rc; ++i) {
           const uint32_t idx = rc - 1 - i;
@@ -248,7 +247,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (my_blocks > 0) mbar_wait(a_empty, (my_blocks - 1) & 1);
       }
-#endif
     }
   } else if (warp == 1) {
     if (cta_rank == 0 && elect_one()) {
@@ -426,11 +424,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         MLP_T(4);
       }
     }
-#ifdef DSG_PAIR_TAIL
     if constexpr (PAIR) {
       if (cc > 0) mbar_wait(g_empty, (cc - 1) & 1);   // the commit after the very last MMA2 (see the producer tail)
     }
-#endif
     if (threadIdx.x == 64) { MLP_T_DUMP(1); }
   } else {
     // ---------------- output warps (4): x += acc2 + b2, 12 chunks of 32 fp32 columns ----------------

@@ -200,12 +200,20 @@ class DINOSeg(nn.Module):
     # -------------------------------------------------------------------------------------
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+        # Trust: a Lightning checkpoint is a pickle (weights_only=False executes what it contains, exactly like the
+        # reference's LightningModule.load_from_checkpoint) - only load checkpoints you would also run as code.
+        # Only a class that cannot be resolved (a package of the training environment that is not installed here:
+        # pytorch_lightning, comet_ml, ...) triggers the tolerant retry; a corrupt file or any other error surfaces
+        # as it is, and if the retry fails too the ORIGINAL error is raised.
         try:
             ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
-        except Exception:
-            with open(checkpoint_path, "rb") as f:
-                ckpt = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=False,
-                                  pickle_module=_tolerant_pickle)
+        except (ModuleNotFoundError, AttributeError, pickle.UnpicklingError) as first_error:
+            try:
+                with open(checkpoint_path, "rb") as f:
+                    ckpt = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=False,
+                                      pickle_module=_tolerant_pickle)
+            except Exception:
+                raise first_error
         hp = dict(ckpt.get("hyper_parameters", {}))
         hp.update(kwargs)
         allowed = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]

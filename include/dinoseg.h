@@ -39,7 +39,9 @@ typedef struct dinoseg_cfg {
   int32_t n_classes;  /* <= 16 */
   int32_t head_h1;    /* 200 (MLP head, pl_torch_modules.py:113) */
   int32_t head_h2;    /* 100 (pl_torch_modules.py:114) */
-  int32_t head_kind;  /* 0 = 'mlp' head (pl_torch_modules.py:108-124) */
+  int32_t head_kind;  /* 0 = 'mlp' head: layer_1 / layer_2 / layer_3 (pl_torch_modules.py:108-124);
+                       * 1 = 'linear' head: one Linear(embed_dim, n_classes) stored as clf.layer_1,
+                       *     head_h1 / head_h2 are ignored (pl_torch_modules.py:127-138) */
   float ln_eps;       /* 1e-6 (vision_transformer.py:303) */
 } dinoseg_cfg;
 

@@ -40,6 +40,10 @@ CASES = [
     ("b8_nb4_240_trained", "vit_base", 4, 240, 1, "trained_like", 6),
     ("b8_nb4_240_refinit", "vit_base", 4, 240, 1, "reference_init", 8),
     ("s8_nb1_240_linear5_refinit", "vit_small", 1, 240, 2, "reference_init", 9),      # head='linear', 5 classes
+    # BASELINE.json configs 4 and 5 at their full per-frame shape (14401 tokens / ViT-B at 3601 tokens); two frames each,
+    # which are also frames 0 and 1 of the batch-16 / batch-32 runs of the GPU tests (make_frames fills frame by frame)
+    ("s8_nb3_960_b2_refinit", "vit_small", 3, 960, 2, "reference_init", 12),
+    ("b8_nb4_480_b2_refinit", "vit_base", 4, 480, 2, "reference_init", 13),
 ]
 
 
@@ -81,10 +85,11 @@ def run_case(plm, vt, name, arch, n_blocks, res, batch, variant, seed):
     m.set_resolution(res)
     g = res // 8
     with torch.no_grad():
-        lp = torch.cat([m(x[b:b + 1]) for b in range(batch)], dim=0) if res >= 480 else m(x)
+        big = res >= 480          # one frame at a time: the reference materialises [B, H, N, N] attention matrices
+        lp = torch.cat([m(x[b:b + 1]) for b in range(batch)], dim=0) if big else m(x)
         tokens = m.dino.prepare_tokens(x)
-        blk0 = m.dino.blocks[0](tokens)
-        normed = m.dino(x)
+        blk0 = torch.cat([m.dino.blocks[0](tokens[b:b + 1]) for b in range(batch)], dim=0) if big else m.dino.blocks[0](tokens)
+        normed = torch.cat([m.dino(x[b:b + 1]) for b in range(batch)], dim=0) if big else m.dino(x)
         pos = m.dino.interpolate_pos_encoding(tokens, res, res)[0].detach()
         # CLS row of the last block's attention (vision_transformer.py:273-280), small cases only (N x N is materialised)
         cls_attn = m.dino.get_last_selfattention(x)[:, :, 0, :].numpy().astype(np.float32) if res <= 240 else np.zeros(0, np.float32)

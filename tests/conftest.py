@@ -43,4 +43,6 @@ GOLDEN_CASES = [
     "s8_nb1_240_refinit", "s8_nb3_480_trained", "s8_nb3_240_b2_trained", "s8_nb2_224_trained",
     "s8_nb1_64_trained", "s8_nb3_480_refinit", "b8_nb4_240_trained", "b8_nb4_240_refinit",
     "s8_nb1_240_linear5_refinit",
+    # BASELINE.json configs[3] / configs[4] at their full per-frame shape (two frames each)
+    "s8_nb3_960_b2_refinit", "b8_nb4_480_b2_refinit",
 ]

@@ -244,6 +244,43 @@ def test_full_size_batch_properties():
     assert agree >= MIN_LABEL_AGREEMENT
 
 
+@pytest.mark.parametrize("name,batch", [("s8_nb3_960_b2_refinit", 16), ("b8_nb4_480_b2_refinit", 32)])
+def test_baseline_configs_4_and_5_at_full_batch(name, batch):
+    """BASELINE.json configs[3] (ViT-S/8, 3 blocks, 960 px = 14401 tokens, batch 16) and configs[4]'s per-GPU shape
+    (ViT-B/8, 4 blocks, 480 px, batch 32) at FULL batch: frames 0 and 1 of the batch are the two frames the unmodified
+    reference was run on (tests/golden, oracle/make_golden.py; vision_transformer.py:80-107 at N = 14401, :307-311 +
+    pl_torch_modules.py:108-124 for ViT-B), and any sub-batch must reproduce its slice of the full batch bit for bit
+    (attention work-item plan, dual tail items and GEMM tiles change with the batch size; results must not)."""
+    gd = load_golden(name)
+    meta = gd["meta"]
+    m, cfg, sd = _model(meta["arch"], meta["n_blocks"], meta["seed"], meta["variant"], meta["n_classes"])
+    res, g = meta["res"], meta["res"] // 8
+    n = g * g
+    x = synthetic.make_frames(batch, res, meta["seed"])
+    assert torch.equal(x[:2], synthetic.make_frames(2, res, meta["seed"]))       # the golden's frames
+    xd = x.cuda()
+    lp, low, lab = m.infer(xd, want_logprobs=True, want_lowres=True, want_labels=True)
+    lp2, low2, _ = m.infer(xd, want_logprobs=True, want_lowres=True)
+    torch.cuda.synchronize()
+    assert torch.equal(lp, lp2) and torch.equal(low, low2) and torch.isfinite(lp).all()
+    got = lp[:2 * n].cpu().numpy()
+    max_abs = _compare_logprobs(name + f"_b{batch}", got, gd["logprobs"], meta["variant"])
+    agree = float((low[:2].cpu().numpy() == gd["low"]).mean())
+    _record(case=name + f"_b{batch}", label_agreement=agree)
+    assert agree >= MIN_LABEL_AGREEMENT, (name, agree)
+    srt = np.sort(gd["logprobs"], axis=1)
+    margin = (srt[:, -1] - srt[:, -2]).reshape(gd["low"].shape)
+    assert (margin[low[:2].cpu().numpy() != gd["low"]] <= 2 * max_abs + 1e-6).all()
+    p = 480 // g
+    assert torch.equal(lab, low.long().repeat_interleave(p, dim=1).repeat_interleave(p, dim=2))
+    assert torch.equal(low.reshape(-1).long(), lp.argmax(1))
+    for sl in (slice(0, 2), slice(batch // 2 - 1, batch // 2 + 2), slice(batch - 1, batch)):
+        lps, lows, _ = m.infer(xd[sl].contiguous(), want_logprobs=True, want_lowres=True)
+        torch.cuda.synchronize()
+        assert torch.equal(lps, lp[sl.start * n:sl.stop * n]), sl
+        assert torch.equal(lows, low[sl]), sl
+
+
 def test_host_entry_point_matches_device_path():
     """dinoseg_predict_host (pinned host buffers in/out) == dinoseg_forward on device buffers, bit for bit."""
     m, cfg, sd = _model("vit_small", 2, 5, "trained_like")

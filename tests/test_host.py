@@ -106,6 +106,43 @@ def test_load_from_checkpoint_roundtrip(tmp_path):
         DINOSeg.load_from_checkpoint(str(path))
 
 
+def test_load_from_checkpoint_with_classes_of_packages_that_are_not_installed(tmp_path):
+    """A real PL checkpoint pickles objects of the training environment (e.g. a comet logger): the tolerant unpickler
+    (model.py::_TolerantUnpickler) replaces classes that cannot be resolved by inert placeholders and the weights still
+    load; a file that is simply corrupt raises the ORIGINAL error instead of being masked by the retry."""
+    import importlib
+    import types
+    cfg = synthetic.make_config("vit_small", 1, 7)
+    sd = synthetic.init_state_dict(cfg, 4, "reference_init")
+    mod = types.ModuleType("some_training_only_package")
+    class CometLogger:                                   # lives in a module that will not exist at load time
+        def __init__(self):
+            self.key = "secret"
+    CometLogger.__module__ = "some_training_only_package"
+    CometLogger.__qualname__ = "CometLogger"
+    mod.CometLogger = CometLogger
+    sys.modules["some_training_only_package"] = mod
+    path = tmp_path / "pl.ckpt"
+    try:
+        hp = dict(head="mlp", n_blocks=1, n_classes=7, comet_logger=CometLogger(), data_path="d", write_path="w")
+        torch.save({"state_dict": sd, "hyper_parameters": hp, "callbacks": {"logger": CometLogger()}}, path)
+    finally:
+        del sys.modules["some_training_only_package"]
+    with pytest.raises(ModuleNotFoundError):             # the plain load cannot resolve the class ...
+        torch.load(path, map_location="cpu", weights_only=False)
+    m = DINOSeg.load_from_checkpoint(str(path))          # ... the drop-in loader can
+    assert m.n_blocks == 1 and m.head == "mlp"
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert type(m.comet_logger).__name__ == "CometLogger" and not hasattr(m.comet_logger, "key")   # inert placeholder
+    # a corrupt file is reported as such (no tolerant retry, no placeholder objects)
+    bad = tmp_path / "corrupt.ckpt"
+    bad.write_bytes(path.read_bytes()[:2000])
+    with pytest.raises(Exception) as ei:
+        DINOSeg.load_from_checkpoint(str(bad))
+    assert not isinstance(ei.value, (KeyError, TypeError)), ei.value
+
+
 def test_unsupported_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
         DINOSeg(head="mlp", backbone="cnn1")
@@ -252,18 +289,53 @@ def test_bench_stall_watchdog_ends_the_run():
     assert "stalled" in r["error"]
 
 
-def test_bench_supervisor_retries_a_stalled_single_gpu_run_once():
-    """Single-GPU runs execute in a child process; a child that stalls is killed, the run repeated once, and after a
-    second stall the parent reports the failure instead of hanging."""
+def test_bench_never_retries_a_stalled_run():
+    """The B200 arm has no supervisor: a run that stalls ends ONCE with the error line and exit code 3 (a retry in the
+    measurement harness would hide exactly the failure a user would hit), and the process that measures is the
+    process that was started (no child, no second attempt)."""
     import json
     env = dict(os.environ, DINOSEG_BENCH_TEST_STALL="1")
     env.pop("WORLD_SIZE", None)
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--stall-limit", "1.5"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert p.returncode == 3, (p.returncode, p.stderr[-500:])
-    assert p.stderr.count("no result after") == 2 and "retrying once" in p.stderr
+    assert p.stderr.count("no result after") == 1 and "retry" not in p.stderr
     r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
-    assert "failed" in r["error"] and "stalled" in r["error"]
+    assert "stalled" in r["error"] and "attempt" not in r
+    with open(os.path.join(ROOT, "bench.py")) as f:
+        src = f.read()
+    assert "def supervise" not in src and "CDLL" not in src
+
+
+def test_bench_default_batch_follows_baseline_configs():
+    """configs[1]: 64 frames on one GPU; configs[2]: 512 frames sharded across 2 / 4 / 8 GPUs (strong scaling)."""
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    old_argv, old_ws = sys.argv, os.environ.get("WORLD_SIZE")
+    try:
+        for world, flags, want in ((1, [], (64, "weak")), (2, [], (256, "strong")), (4, [], (128, "strong")),
+                                   (8, [], (64, "strong")), (8, ["--batch", "64"], (64, "weak")),
+                                   (4, ["--global-batch", "512"], (128, "strong")), (1, ["--global-batch", "512"], (512, "strong"))):
+            os.environ["WORLD_SIZE"] = str(world)
+            sys.argv = ["bench.py"] + flags
+            a = bench.parse_args()
+            assert (a.batch, a.scaling) == want, (world, flags, a.batch, a.scaling)
+    finally:
+        sys.argv = old_argv
+        if old_ws is None:
+            os.environ.pop("WORLD_SIZE", None)
+        else:
+            os.environ["WORLD_SIZE"] = old_ws
+
+
+def test_bench_reads_the_attention_traffic_from_profiles():
+    """roofline.traffic comes from the committed ncu summary, not from a literal in bench.py."""
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    traffic, src, _ = bench.ncu_attention_traffic()
+    assert src is not None and src.startswith("profiles/") and 5e8 < traffic < 1e9, (traffic, src)
 
 
 def test_product_code_never_imports_the_oracle():
