@@ -39,6 +39,10 @@ SIGNATURES = {
                                      C.c_void_p]),
     "dinoseg_predict_host_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                           C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dinoseg_predict_host_submit": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dinoseg_predict_host_submit_u8": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                                   C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dinoseg_predict_host_wait": (C.c_int, [C.c_void_p, C.c_int64]),
     "dinoseg_set_host_chunk": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_cls_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dinoseg_argmax_replicate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -324,7 +324,7 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
   constexpr float LOG2E = ATT_LOG2E;
   const int t = (warp - 4) >> 3;                   // query tile of this warp
   const int rbase = (warp & 3) * 32 + (((warp - 4) >> 2) & 1) * 16;   // first of the warp's 16 rows (= TMEM lanes)
-  const int qd = lane & 3, r8 = lane >> 2;
+  const int qd = lane & 3;                         // this thread's rows: rbase + lane / 4 and rbase + lane / 4 + 8
   const uint32_t lane_base = tmem_base + (uint32_t(rbase) << 16);
   const uint32_t s_addr = lane_base + ATT_S_COL0 + uint32_t(t * 128);
   const uint32_t p_addr = lane_base + ATT_P_COL0 + uint32_t(t * 64);
@@ -338,7 +338,7 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
     const int bh = t ? I.bh[1] : I.bh[0];
     const int h = bh % p.H, b = bh / p.H;
     const int q0 = t ? I.q0[1] : I.q0[0];
-    float m0 = 0.f, m1 = 0.f;                      // (stale) running maxima of rows r8 and r8 + 8 (raw scores)
+    float m0 = 0.f, m1 = 0.f;                      // (stale) running maxima of this thread's two rows (raw scores)
     float l0 = 0.f, l1 = 0.f;                      // this thread's share of the running row sums of exp(s - m)
 
     for (int j = 0; j < num_tiles; ++j, ++sc) {
@@ -501,8 +501,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // registers move from the producer warpgroup to the softmax warps: 128*80 + 256*208 (SMW = 4) and
-    // 128*56 + 512*112 (SMW = 8) both fit the 64 K registers of an SM
+    // Registers move from the producer warpgroup to the softmax warps.  The budget is the CTA's register pool AT LAUNCH
+    // (threads x the kernel's register count), not the SM's 64 K: 384 x 168 = 64512 >= 128*80 + 256*208 (SMW = 4);
+    // 640 x 96 = 61440 >= 128*56 + 512*104 (SMW = 8).  A setmaxnreg.inc beyond the pool blocks forever.
     if constexpr (SMW == 4) setmaxnreg_dec<80>(); else setmaxnreg_dec<56>();
     if (warp == 0 && elect_one()) {
       // ------------------------------ TMA producer ------------------------------
@@ -621,7 +622,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       setmaxnreg_inc<208>();
       att_softmax_rows(p, tmem_base, ab, warp, lane, num_tiles);
     } else {
-      setmaxnreg_inc<112>();
+      setmaxnreg_inc<104>();
       att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
     }
   }

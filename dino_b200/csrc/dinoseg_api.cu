@@ -547,11 +547,27 @@ struct dinoseg {
   int host_chunk = 0;               // frames per pipeline chunk; 0 = automatic (see pick_host_chunk)
   // host label maps: 1 = copy the low-res maps (g*g bytes per frame) to the host and expand them to int64 there with
   // worker threads (what the reference does with np.kron); 0 = replicate on the GPU and copy 8*(g*p)^2 bytes per frame
-  int host_expand = 0;
+  // -1 (default) = decide from the host cores this rank can use (see host_expand_on)
+  int host_expand = -1;
   HostPool* pool = nullptr;
-  uint8_t* low_stage = nullptr;     // pinned [batch, g*g]
-  size_t low_stage_cap = 0;
-  std::vector<cudaEvent_t> chunk_done;
+  bool pool_failed = false;         // no worker thread could be created: DMA path from now on
+  // outstanding dinoseg_predict_host_submit calls (ring of slots; id 0 = free)
+  static constexpr int kTickets = 4;
+  struct Ticket {
+    int64_t id = 0;
+    int nlanes = 0;
+    cudaEvent_t lane_done[kLanes] = {};
+    bool expand = false;
+    std::vector<int> plan;            // frames per chunk
+    std::vector<cudaEvent_t> chunk_done;
+    uint8_t* low_stage = nullptr;     // pinned [batch, g*g]: low-res maps of this submission (expand mode)
+    size_t low_stage_cap = 0;
+    uint8_t* host_lowres = nullptr;
+    int64_t* host_labels = nullptr;
+    int g = 0, p_rep = 0;
+  };
+  Ticket tickets[kTickets];
+  int64_t next_ticket = 1;
 };
 
 namespace {
@@ -699,7 +715,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     h->gemm_pair = atoi(mode) != 0;
     h->mlp_pair = h->fused_mlp && atoi(mode) != 0;
   }
-  if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0;   // measurement override
+  if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0 ? 1 : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
@@ -801,8 +817,11 @@ void dinoseg_destroy(dinoseg_t* h) {
   }
   if (h->host_start) cudaEventDestroy(h->host_start);
   delete h->pool;
-  if (h->low_stage) cudaFreeHost(h->low_stage);
-  for (cudaEvent_t e : h->chunk_done) cudaEventDestroy(e);
+  for (dinoseg::Ticket& t : h->tickets) {
+    if (t.low_stage) cudaFreeHost(t.low_stage);
+    for (cudaEvent_t e : t.chunk_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : t.lane_done) if (e) cudaEventDestroy(e);
+  }
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
@@ -1123,19 +1142,78 @@ static int pick_host_chunk(const dinoseg* h, int batch) {
   return best;
 }
 
+// host cores this process may use, divided by the ranks that share the host (torchrun exports LOCAL_WORLD_SIZE)
+static int host_cores_per_rank() {
+  int cpus = 0;
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+  if (cpus <= 0) cpus = int(std::thread::hardware_concurrency());
+  const char* lw = getenv("LOCAL_WORLD_SIZE");
+  const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+  return cpus / ranks;
+}
+
+// Label maps of the host entry points: expand on the host (low-res maps over PCIe, int64 maps written by worker
+// threads) or replicate on the GPU and copy the int64 maps out.  Automatic choice: host expansion needs cores - with
+// >= 8 per rank it measured +2.5 % end to end (one GPU, 16 cores), with 4 per rank (eight GPUs on a 32-vCPU host)
+// the workers compete with the ranks' own threads and the DMA path is the safer one.
+static bool host_expand_on(const dinoseg* h) {
+  if (h->pool_failed) return false;
+  if (h->host_expand >= 0) return h->host_expand != 0;
+  static const bool enough = host_cores_per_rank() >= 8;
+  return enough;
+}
+
+static dinoseg::Ticket* find_ticket(dinoseg_t* h, int64_t id) {
+  for (dinoseg::Ticket& t : h->tickets)
+    if (t.id == id) return &t;
+  return nullptr;
+}
+
+// Completes one submission: host-side expansion of its label maps (expand mode), then its lanes' last copies.
+static int ticket_wait(dinoseg_t* h, dinoseg::Ticket& t) {
+  int rc = 0;
+  if (t.expand) {
+    // chunk by chunk, as the low-res maps arrive: one expansion task per frame
+    const size_t P = size_t(t.g) * t.g, W = size_t(t.g) * t.p_rep;
+    int f0 = 0;
+    for (size_t c = 0; c < t.plan.size(); f0 += t.plan[c], ++c) {
+      if (t.plan[c] <= 0) continue;
+      if (cudaEventSynchronize(t.chunk_done[c]) != cudaSuccess) { rc = -1; break; }
+      if (t.host_lowres) memcpy(t.host_lowres + size_t(f0) * P, t.low_stage + size_t(f0) * P, size_t(t.plan[c]) * P);
+      for (int i = 0; i < t.plan[c]; ++i) {
+        const uint8_t* low = t.low_stage + size_t(f0 + i) * P;
+        int64_t* out = t.host_labels + size_t(f0 + i) * W * W;
+        const int g = t.g, prep = t.p_rep;
+        h->pool->submit([low, out, g, prep] { expand_labels_host(low, out, g, prep); });
+      }
+    }
+    h->pool->wait_all();
+  }
+  for (int k = 0; k < t.nlanes; ++k)
+    if (cudaEventSynchronize(t.lane_done[k]) != cudaSuccess) rc = -1;
+  t.id = 0;
+  if (rc != 0) { h->err = "dinoseg_predict_host_wait: a CUDA operation of the submission failed"; }
+  return rc;
+}
+
 // Shared implementation of the host entry points: `host_frames` are fp32 normalised frames (pp == nullptr) or raw
-// uint8 HWC frames of src_h x src_w pixels (pp != nullptr).
-static int predict_host_impl(dinoseg_t* h, const void* host_frames, const PreprocParams* pp, int batch,
-                             uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who) {
+// uint8 HWC frames of src_h x src_w pixels (pp != nullptr).  Enqueues the whole submission and returns its ticket
+// (> 0) without waiting for the GPU; < 0 on error (nothing is left in flight then).
+static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, const PreprocParams* pp, int batch,
+                                        uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who) {
   if (!h) return -1;
   if (h->res == 0) DSG_FAIL(h, "%s: call dinoseg_set_resolution first", who);
   if (!host_frames || batch <= 0) DSG_FAIL(h, "%s: bad arguments", who);
+  dinoseg::Ticket* tk = find_ticket(h, 0);
+  if (!tk) DSG_FAIL(h, "%s: %d submissions are outstanding; call dinoseg_predict_host_wait first", who, dinoseg::kTickets);
   DSG_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // The batch is cut into chunks that go round-robin through three lanes (stream + staging + workspace
   // each): H2D copy, forward and D2H copy of a chunk are ordered on its lane's stream, and the copies
   // of one lane overlap the kernels of the other.  Frames are independent, so chunking does not change
-  // any result bit.
+  // any result bit.  Consecutive submissions queue behind each other on the same lanes: the first H2D copy of
+  // submission k+1 overlaps the last kernels and the last D2H copy of submission k.
   const int chunk = pick_host_chunk(h, batch);
   const size_t frame_bytes = pp ? size_t(pp->src_h) * pp->src_w * 3 : size_t(3) * h->res * h->res * sizeof(float);
   const size_t W = size_t(h->g) * h->p_rep;
@@ -1151,7 +1229,8 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
   };
   // chunk plan: a SHORT first chunk (its H2D copy is the pipeline fill that nothing overlaps) and a short last one
   // (its D2H copy is the drain), full chunks in between
-  std::vector<int> plan;
+  std::vector<int>& plan = tk->plan;
+  plan.clear();
   if (batch <= chunk) {
     plan.push_back(batch);
   } else {
@@ -1166,47 +1245,40 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
   const int nchunks = int(plan.size());
   const int nlanes = nchunks < dinoseg::kLanes ? nchunks : dinoseg::kLanes;
   const bool want_labels = host_labels && label_elems;
-  // Label maps: the int64 [g*p, g*p] map is 512x the size of the low-res map it replicates.  With host_expand the
+  // Label maps: the int64 [g*p, g*p] map is 512x the size of the low-res map it replicates.  With host expansion the
   // GPU ships the low-res maps (3.6 KB per frame at 480 px) and worker threads expand them into the caller's buffer
-  // while later chunks are still computing, instead of 1.84 MB per frame over PCIe.
-  bool expand = want_labels && h->host_expand != 0;
+  // (in dinoseg_predict_host_wait, while later submissions are already computing), instead of 1.84 MB per frame over PCIe.
+  bool expand = want_labels && host_expand_on(h);
   if (expand && !h->pool) {
-    {
-      int cpus = 0;
-      cpu_set_t set;
-      if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
-      if (cpus <= 0) cpus = int(std::thread::hardware_concurrency());
-      const char* lw = getenv("LOCAL_WORLD_SIZE");          // torchrun: ranks sharing this host's cores
-      const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
-      int n = cpus / ranks;
-      if (const char* e = getenv("DINOSEG_HOST_THREADS")) n = atoi(e);
-      n = n < 1 ? 1 : (n > 8 ? 8 : n);
-      try {
-        h->pool = new HostPool(n);
-      } catch (...) {                              // no threads to be had: GPU replication + whole-map copies
-        h->pool = nullptr;
-        h->host_expand = 0;
-        expand = false;
-      }
+    int n = host_cores_per_rank();
+    if (const char* e = getenv("DINOSEG_HOST_THREADS")) n = atoi(e);
+    n = n < 1 ? 1 : (n > 8 ? 8 : n);
+    try {
+      h->pool = new HostPool(n);
+    } catch (...) {                              // no threads to be had: GPU replication + whole-map copies
+      h->pool = nullptr;
+      h->pool_failed = true;
+      expand = false;
     }
   }
   if (expand) {
     const size_t need = size_t(batch) * h->P;
-    if (need > h->low_stage_cap) {
-      if (h->low_stage) { cudaFreeHost(h->low_stage); h->low_stage = nullptr; h->low_stage_cap = 0; }
-      DSG_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&h->low_stage), need, cudaHostAllocDefault));
-      h->low_stage_cap = need;
+    if (need > tk->low_stage_cap) {
+      if (tk->low_stage) { cudaFreeHost(tk->low_stage); tk->low_stage = nullptr; tk->low_stage_cap = 0; }
+      DSG_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&tk->low_stage), need, cudaHostAllocDefault));
+      tk->low_stage_cap = need;
     }
-    while (int(h->chunk_done.size()) < nchunks) {
+    while (int(tk->chunk_done.size()) < nchunks) {
       cudaEvent_t e;
       DSG_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      h->chunk_done.push_back(e);
+      tk->chunk_done.push_back(e);
     }
   }
   for (int k = 0; k < nlanes; ++k) {
     HostLane& l = h->lanes[k];
     if (!l.stream) DSG_CUDA(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     if (!l.done) DSG_CUDA(h, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    if (!tk->lane_done[k]) DSG_CUDA(h, cudaEventCreateWithFlags(&tk->lane_done[k], cudaEventDisableTiming));
     const size_t ws_before = l.ws_cap;
     DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.frames), &l.frames_cap, size_t(chunk) * frame_bytes));
     DSG_CUDA(h, grow(l, &l.ws, &l.ws_cap, wbytes));
@@ -1215,56 +1287,81 @@ static int predict_host_impl(dinoseg_t* h, const void* host_frames, const Prepro
       DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.labels), &l.labels_cap, size_t(chunk) * label_elems * sizeof(int64_t)));
     if (l.ws_cap != ws_before) l.bufs.base = nullptr;
   }
-  // lanes start after whatever the caller queued on its stream
-  DSG_CUDA(h, cudaEventRecord(h->host_start, s));
-  for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamWaitEvent(h->lanes[k].stream, h->host_start, 0));
-  int f0 = 0;
-  for (int c = 0; c < nchunks; f0 += plan[c], ++c) {
-    HostLane& l = h->lanes[c % nlanes];
-    const int nb = plan[c];
-    if (nb <= 0) continue;
-    DSG_CUDA(h, cudaMemcpyAsync(l.frames, static_cast<const uint8_t*>(host_frames) + size_t(f0) * frame_bytes,
-                                size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, l.stream));
-    if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
-    if (forward_impl(h, l.bufs, pp ? nullptr : l.frames, pp ? reinterpret_cast<const uint8_t*>(l.frames) : nullptr, pp, nb,
-                     nullptr, l.lowres, (want_labels && !expand) ? l.labels : nullptr, l.stream) != 0)
-      return -1;
-    if (expand) {
-      DSG_CUDA(h, cudaMemcpyAsync(h->low_stage + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
-                                  l.stream));
-      DSG_CUDA(h, cudaEventRecord(h->chunk_done[c], l.stream));
-      continue;
-    }
-    if (host_lowres)
-      DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
-                                  l.stream));
-    if (want_labels)
-      DSG_CUDA(h, cudaMemcpyAsync(host_labels + size_t(f0) * label_elems, l.labels,
-                                  size_t(nb) * label_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
-  }
-  for (int k = 0; k < nlanes; ++k) {
-    DSG_CUDA(h, cudaEventRecord(h->lanes[k].done, h->lanes[k].stream));
-    DSG_CUDA(h, cudaStreamWaitEvent(s, h->lanes[k].done, 0));   // later work on the caller's stream is ordered after us
-  }
-  if (expand) {
-    // chunk by chunk, as the low-res maps arrive: one expansion task per frame
-    const int g = h->g, prep = h->p_rep;
-    const size_t P = h->P;
-    f0 = 0;
+  // From here on work is in flight: every error exit drains the lanes first, so that the caller may free its buffers.
+  auto enqueue = [&]() -> int {
+    // lanes start after whatever the caller queued on its stream
+    DSG_CUDA(h, cudaEventRecord(h->host_start, s));
+    for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamWaitEvent(h->lanes[k].stream, h->host_start, 0));
+    int f0 = 0;
     for (int c = 0; c < nchunks; f0 += plan[c], ++c) {
-      if (plan[c] <= 0) continue;
-      DSG_CUDA(h, cudaEventSynchronize(h->chunk_done[c]));
-      if (host_lowres) memcpy(host_lowres + size_t(f0) * P, h->low_stage + size_t(f0) * P, size_t(plan[c]) * P);
-      for (int i = 0; i < plan[c]; ++i) {
-        const uint8_t* low = h->low_stage + size_t(f0 + i) * P;
-        int64_t* out = host_labels + size_t(f0 + i) * label_elems;
-        h->pool->submit([low, out, g, prep] { expand_labels_host(low, out, g, prep); });
+      HostLane& l = h->lanes[c % nlanes];
+      const int nb = plan[c];
+      if (nb <= 0) continue;
+      DSG_CUDA(h, cudaMemcpyAsync(l.frames, static_cast<const uint8_t*>(host_frames) + size_t(f0) * frame_bytes,
+                                  size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, l.stream));
+      if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
+      if (forward_impl(h, l.bufs, pp ? nullptr : l.frames, pp ? reinterpret_cast<const uint8_t*>(l.frames) : nullptr, pp, nb,
+                       nullptr, l.lowres, (want_labels && !expand) ? l.labels : nullptr, l.stream) != 0)
+        return -1;
+      if (expand) {
+        DSG_CUDA(h, cudaMemcpyAsync(tk->low_stage + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
+                                    l.stream));
+        DSG_CUDA(h, cudaEventRecord(tk->chunk_done[c], l.stream));
+        continue;
       }
+      if (host_lowres)
+        DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
+                                    l.stream));
+      if (want_labels)
+        DSG_CUDA(h, cudaMemcpyAsync(host_labels + size_t(f0) * label_elems, l.labels,
+                                    size_t(nb) * label_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
     }
-    h->pool->wait_all();
+    // (the caller's stream is NOT made to wait for the lanes: the results are host buffers, complete when
+    // dinoseg_predict_host_wait returns, and a wait here would serialise consecutive submissions)
+    for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaEventRecord(tk->lane_done[k], h->lanes[k].stream));
+    return 0;
+  };
+  if (enqueue() != 0) {
+    const std::string why = h->err;
+    for (int k = 0; k < nlanes; ++k)
+      if (h->lanes[k].stream) cudaStreamSynchronize(h->lanes[k].stream);
+    if (h->pool) h->pool->wait_all();
+    (void)cudaGetLastError();
+    h->err = why;
+    return -1;
   }
-  for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamSynchronize(h->lanes[k].stream));
-  return 0;
+  tk->nlanes = nlanes;
+  tk->expand = expand;
+  tk->host_lowres = host_lowres;
+  tk->host_labels = host_labels;
+  tk->g = h->g;
+  tk->p_rep = h->p_rep;
+  tk->id = h->next_ticket++;
+  return tk->id;
+}
+
+static int predict_host_wait_impl(dinoseg_t* h, int64_t ticket) {
+  if (!h) return -1;
+  DSG_CUDA(h, cudaSetDevice(h->device));
+  if (ticket == 0) {                     // everything outstanding, oldest first
+    int rc = 0;
+    for (;;) {
+      dinoseg::Ticket* oldest = nullptr;
+      for (dinoseg::Ticket& t : h->tickets)
+        if (t.id != 0 && (!oldest || t.id < oldest->id)) oldest = &t;
+      if (!oldest) return rc;
+      if (ticket_wait(h, *oldest) != 0) rc = -1;
+    }
+  }
+  dinoseg::Ticket* t = ticket > 0 ? find_ticket(h, ticket) : nullptr;
+  if (!t) DSG_FAIL(h, "dinoseg_predict_host_wait: unknown ticket %lld (already waited for?)", (long long)ticket);
+  return ticket_wait(h, *t);
+}
+
+static int predict_host_impl(dinoseg_t* h, const void* host_frames, const PreprocParams* pp, int batch,
+                             uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who) {
+  const int64_t t = predict_host_submit_impl(h, host_frames, pp, batch, host_lowres, host_labels, stream, who);
+  return t < 0 ? -1 : predict_host_wait_impl(h, t);
 }
 
 static int make_preproc(dinoseg_t* h, int src_h, int src_w, const float* mean, const float* std_, PreprocParams* pp) {
@@ -1290,6 +1387,24 @@ int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames, int batch,
   if (make_preproc(h, src_h, src_w, mean, std_, &pp) != 0) return -1;
   return predict_host_impl(h, host_frames, &pp, batch, host_lowres, host_labels, stream, "dinoseg_predict_host_u8");
 }
+
+int64_t dinoseg_predict_host_submit(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
+                                    int64_t* host_labels, void* stream) {
+  return predict_host_submit_impl(h, host_frames, nullptr, batch, host_lowres, host_labels, stream,
+                                  "dinoseg_predict_host_submit");
+}
+
+int64_t dinoseg_predict_host_submit_u8(dinoseg_t* h, const uint8_t* host_frames, int batch, int src_h, int src_w,
+                                       const float* mean, const float* std_, uint8_t* host_lowres, int64_t* host_labels,
+                                       void* stream) {
+  if (!h) return -1;
+  PreprocParams pp;
+  if (make_preproc(h, src_h, src_w, mean, std_, &pp) != 0) return -1;
+  return predict_host_submit_impl(h, host_frames, &pp, batch, host_lowres, host_labels, stream,
+                                  "dinoseg_predict_host_submit_u8");
+}
+
+int dinoseg_predict_host_wait(dinoseg_t* h, int64_t ticket) { return predict_host_wait_impl(h, ticket); }
 
 int dinoseg_forward_u8(dinoseg_t* h, const uint8_t* frames, int batch, int src_h, int src_w, const float* mean,
                        const float* std_, float* logprobs, uint8_t* lowres, int64_t* labels, void* workspace,
@@ -1321,12 +1436,12 @@ int dinoseg_expand_labels_host(const uint8_t* lowres, int batch, int g, int p, i
 int dinoseg_get_pair_kernels(const dinoseg_t* h) { return h ? (h->gemm_pair ? 1 : 0) | (h->mlp_pair ? 2 : 0) : -1; }
 
 int dinoseg_set_host_expand(dinoseg_t* h, int on) {
-  if (!h || on < 0 || on > 1) return -1;
-  h->host_expand = on;
+  if (!h || on < -1 || on > 1) return -1;
+  h->host_expand = on;              // -1 = automatic (cores per rank), 0 = GPU replication + DMA, 1 = host expansion
   return 0;
 }
 
-int dinoseg_get_host_expand(const dinoseg_t* h) { return h ? h->host_expand : -1; }
+int dinoseg_get_host_expand(const dinoseg_t* h) { return h ? (host_expand_on(h) ? 1 : 0) : -1; }
 
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk) {
   if (!h || frames_per_chunk < 0) return -1;

@@ -194,6 +194,7 @@ class DINOSeg(nn.Module):
         self._fingerprint = None
         self._lib_res = None
         self._workspace = None
+        self._pending = {}            # ticket -> (frames, out) of predict_batch_async submissions in flight
 
     # -------------------------------------------------------------------------------------
     # construction from a checkpoint (replaces LightningModule.load_from_checkpoint, README.md:31)
@@ -258,6 +259,9 @@ class DINOSeg(nn.Module):
     def _release(self):
         if self._handle is not None:
             try:
+                if getattr(self, "_pending", None):
+                    _lib.load().dinoseg_predict_host_wait(self._handle, 0)
+                    self._pending.clear()
                 _lib.load().dinoseg_destroy(self._handle)
             except Exception:
                 pass
@@ -449,32 +453,75 @@ class DINOSeg(nn.Module):
         self._check(rc, "dinoseg_forward_u8")
         return lp, low, lab
 
-    def predict_batch_u8(self, frames_u8, resolution=None, output="labels", out=None):
-        """Batched predict() on raw HOST frames: uint8 [B,H,W,3] (ideally pinned) -> numpy label maps; resize,
-        normalisation, forward, argmax and replication on the GPU, copies pipelined with the kernels."""
-        if output not in ("labels", "lowres"):
-            raise ValueError(output)
-        lib = self._ensure_handle()
-        if frames_u8.dim() != 4 or frames_u8.shape[3] != 3 or frames_u8.dtype != torch.uint8 or frames_u8.device.type != "cpu":
-            raise ValueError("expected CPU uint8 frames of shape [B,H,W,3]")
-        frames_u8 = frames_u8.contiguous()
-        res = int(self.resolution if resolution is None else resolution)
-        b, sh, sw = int(frames_u8.shape[0]), int(frames_u8.shape[1]), int(frames_u8.shape[2])
-        self._ensure_resolution(lib, res)
-        g = res // 8
+    # -------------------------------------------------------------------------------------
+    # host frames -> host label maps (the library's pipelined host entry points)
+    # -------------------------------------------------------------------------------------
+    def _host_out(self, b, g, output, out):
         p = 480 // g
         shape, dtype = ((b, g * p, g * p), torch.int64) if output == "labels" else ((b, g, g), torch.uint8)
         if out is None:
             out = torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
         elif tuple(out.shape) != shape or out.dtype != dtype or out.device.type != "cpu" or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous CPU tensor of shape {shape} and dtype {dtype}")
-        mean = (C.c_float * 3)(*IMAGENET_MEAN)
-        std = (C.c_float * 3)(*IMAGENET_STD)
-        rc = lib.dinoseg_predict_host_u8(self._handle, frames_u8.data_ptr(), b, sh, sw, mean, std,
-                                         out.data_ptr() if output == "lowres" else None,
-                                         out.data_ptr() if output == "labels" else None, self._stream())
-        self._check(rc, "dinoseg_predict_host_u8")
+        return out
+
+    def _submit_host(self, frames, resolution, output, out):
+        """Enqueue one host batch (fp32 [B,3,r,r] normalised, or uint8 [B,H,W,3] raw) -> ticket."""
+        if output not in ("labels", "lowres"):
+            raise ValueError(output)
+        lib = self._ensure_handle()
+        if frames.device.type != "cpu":
+            raise ValueError("expected CPU frames")
+        if frames.dtype == torch.uint8:
+            if frames.dim() != 4 or frames.shape[3] != 3:
+                raise ValueError("expected CPU uint8 frames of shape [B,H,W,3]")
+            frames = frames.contiguous()
+            res = int(self.resolution if resolution is None else resolution)
+            b, sh, sw = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+        else:
+            if frames.dim() != 4 or frames.shape[1] != 3 or frames.shape[2] != frames.shape[3]:
+                raise ValueError(f"expected frames of shape [B,3,r,r], got {tuple(frames.shape)}")
+            frames = frames.contiguous().float()
+            b, res = int(frames.shape[0]), int(frames.shape[2])
+        self._ensure_resolution(lib, res)
+        out = self._host_out(b, res // 8, output, out)
+        low_ptr = out.data_ptr() if output == "lowres" else None
+        lab_ptr = out.data_ptr() if output == "labels" else None
+        if frames.dtype == torch.uint8:
+            mean = (C.c_float * 3)(*IMAGENET_MEAN)
+            std = (C.c_float * 3)(*IMAGENET_STD)
+            t = lib.dinoseg_predict_host_submit_u8(self._handle, frames.data_ptr(), b, sh, sw, mean, std, low_ptr, lab_ptr,
+                                                   self._stream())
+        else:
+            t = lib.dinoseg_predict_host_submit(self._handle, frames.data_ptr(), b, low_ptr, lab_ptr, self._stream())
+        if t <= 0:
+            raise RuntimeError("dinoseg_predict_host_submit failed: " + _lib.last_error(self._handle))
+        self._pending[t] = (frames, out)          # the library reads / writes these buffers until predict_wait(t)
+        return t
+
+    def predict_batch_async(self, frames, resolution=None, output="labels", out=None):
+        """Asynchronous predict_batch for a caller that streams batches (camera, folder of images): enqueue the batch
+        and return a ticket at once; `predict_wait(ticket)` returns the numpy result.  Up to 4 batches may be in
+        flight; the H2D copy of one overlaps the kernels and the D2H copy of the one before.  frames: CPU fp32
+        [B,3,r,r] (normalised) or CPU uint8 [B,H,W,3] (raw; resized to `resolution` and normalised on the GPU);
+        `frames` and `out` must not be modified before predict_wait returns."""
+        return self._submit_host(frames, resolution, output, out)
+
+    def predict_wait(self, ticket):
+        """Wait for a predict_batch_async submission -> numpy result (int64 [B,g*p,g*p] or uint8 [B,g,g])."""
+        if ticket not in self._pending:
+            raise KeyError(f"unknown ticket {ticket} (already waited for?)")
+        rc = _lib.load().dinoseg_predict_host_wait(self._handle, int(ticket))
+        _, out = self._pending.pop(ticket)
+        self._check(rc, "dinoseg_predict_host_wait")
         return out.numpy()
+
+    def predict_batch_u8(self, frames_u8, resolution=None, output="labels", out=None):
+        """Batched predict() on raw HOST frames: uint8 [B,H,W,3] (ideally pinned) -> numpy label maps; resize,
+        normalisation, forward, argmax and replication on the GPU, copies pipelined with the kernels."""
+        if frames_u8.dtype != torch.uint8 or frames_u8.device.type != "cpu":
+            raise ValueError("expected CPU uint8 frames of shape [B,H,W,3]")
+        return self.predict_wait(self._submit_host(frames_u8, resolution, output, out))
 
     def predict_batch(self, frames, output="labels", out=None):
         """Batched counterpart of predict() for already-normalised frames [B,3,r,r].
@@ -489,22 +536,9 @@ class DINOSeg(nn.Module):
             _, low, lab = self.infer(frames, want_logprobs=False, want_lowres=output == "lowres",
                                      want_labels=output == "labels")
             return lab if output == "labels" else low
-        lib = self._ensure_handle()
-        frames = frames.contiguous().float()
-        b, res = int(frames.shape[0]), int(frames.shape[2])
-        self._ensure_resolution(lib, res)
-        g = res // 8
-        p = 480 // g
-        shape, dtype = ((b, g * p, g * p), torch.int64) if output == "labels" else ((b, g, g), torch.uint8)
-        if out is None:
-            out = torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
-        elif tuple(out.shape) != shape or out.dtype != dtype or out.device.type != "cpu" or not out.is_contiguous():
-            raise ValueError(f"out must be a contiguous CPU tensor of shape {shape} and dtype {dtype}")
-        rc = lib.dinoseg_predict_host(self._handle, frames.data_ptr(), b,
-                                      out.data_ptr() if output == "lowres" else None,
-                                      out.data_ptr() if output == "labels" else None, self._stream())
-        self._check(rc, "dinoseg_predict_host")
-        return out.numpy()
+        if frames.dtype == torch.uint8:
+            raise ValueError("uint8 frames go through predict_batch_u8")
+        return self.predict_wait(self._submit_host(frames, None, output, out))
 
     def profile_enable(self, on=True, kinds=None):
         """Bracket kernel launches of the following forwards with CUDA events (on the launching

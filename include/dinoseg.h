@@ -83,6 +83,20 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
 int dinoseg_predict_host(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
                          int64_t* host_labels, void* stream);
 
+/* Asynchronous form: dinoseg_predict_host_submit enqueues the whole submission (copies and kernels on the library's
+ * streams) and returns a ticket (> 0; < 0 = error) without waiting for the GPU; the host buffers (frames in, label
+ * maps out) must stay valid and untouched until dinoseg_predict_host_wait(h, ticket) has returned 0 (ticket 0 waits for
+ * everything outstanding, oldest first).  Up to 4 submissions may be outstanding; they queue behind each other on the
+ * same streams, so the first H2D copy of one overlaps the last kernels / D2H copy of the one before - what a caller
+ * that streams batches (a camera, a folder of images) wants.  dinoseg_predict_host == submit + wait.
+ * Replaces the boundaries `x.to(self.device)` / `.cpu()` of DINOSeg.predict (pl_torch_modules.py:292, :295). */
+int64_t dinoseg_predict_host_submit(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
+                                    int64_t* host_labels, void* stream);
+int64_t dinoseg_predict_host_submit_u8(dinoseg_t* h, const uint8_t* host_frames_u8, int batch, int src_h, int src_w,
+                                       const float* mean, const float* std_, uint8_t* host_lowres, int64_t* host_labels,
+                                       void* stream);
+int dinoseg_predict_host_wait(dinoseg_t* h, int64_t ticket);
+
 /* The same two calls on RAW camera frames: uint8 RGB, HWC, [batch, src_h, src_w, 3].  Replaces the inference
  * transforms of DINOSeg.predict (pl_torch_modules.py:33-41, :291: albumentations Resize(r, r) -> Normalize(mean, std)
  * -> ToTensorV2) on the GPU, fused into the patch-embed im2col: the bilinear resize reproduces cv2.resize(INTER_LINEAR)
@@ -99,10 +113,12 @@ int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames_u8, int bat
  * whose H2D copy, kernels and D2H copy overlap across two internal streams. */
 int dinoseg_set_host_chunk(dinoseg_t* h, int frames_per_chunk);
 
-/* How the host entry points produce the int64 label maps.  0 (default): the maps are replicated on the GPU and copied
- * out whole (8*(g*p)^2 bytes per frame).  1: the low-res maps (g*g bytes per frame) are copied to the host and expanded
- * there by worker threads into the caller's buffer while later chunks compute - what the reference does with np.kron
- * (pl_torch_modules.py:297-298), 512x fewer bytes over PCIe (+2.5 % e2e on one GPU, +4 % on eight).  Identical bytes. */
+/* How the host entry points produce the int64 label maps.  0: the maps are replicated on the GPU and copied out whole
+ * (8*(g*p)^2 bytes per frame).  1: the low-res maps (g*g bytes per frame) are copied to the host and expanded there by
+ * worker threads into the caller's buffer while later chunks / submissions compute - what the reference does with
+ * np.kron (pl_torch_modules.py:297-298), 512x fewer bytes over PCIe.  Identical bytes either way.  -1 (default):
+ * automatic - host expansion when this rank has at least 8 host cores to itself (cores of the process / ranks per
+ * host), the DMA path otherwise.  dinoseg_get_host_expand returns the mode in effect (0 / 1). */
 int dinoseg_set_host_expand(dinoseg_t* h, int on);
 int dinoseg_get_host_expand(const dinoseg_t* h);
 /* The host-side expansion itself (pure CPU, no device needed): lowres host uint8 [batch, g, g] -> labels host int64

@@ -294,14 +294,47 @@ def test_host_entry_point_matches_device_path():
     # the two ways of producing host label maps (GPU replication + D2H of the whole int64 maps, the default; low-res
     # D2H + expansion by the library's host threads) give the same bytes
     lib = _lib.load()
-    assert lib.dinoseg_get_host_expand(m._handle) == 0
-    assert lib.dinoseg_set_host_expand(m._handle, 1) == 0
-    lab_exp = m.predict_batch(x.pin_memory(), output="labels")
+    assert lib.dinoseg_get_host_expand(m._handle) in (0, 1)   # automatic by default (host cores per rank)
     big = synthetic.make_frames(23, 240, seed=3)               # several chunks, ragged first / last chunk
-    big_exp = m.predict_batch(big.pin_memory(), output="labels")
-    assert lib.dinoseg_set_host_expand(m._handle, 0) == 0
-    assert (lab_exp == lab_host).all()
-    assert (big_exp == m.predict_batch(big.cuda(), output="labels").cpu().numpy()).all()
+    big_dev = m.predict_batch(big.cuda(), output="labels").cpu().numpy()
+    for mode in (1, 0):
+        assert lib.dinoseg_set_host_expand(m._handle, mode) == 0 and lib.dinoseg_get_host_expand(m._handle) == mode
+        assert (m.predict_batch(x.pin_memory(), output="labels") == lab_host).all()
+        assert (m.predict_batch(big.pin_memory(), output="labels") == big_dev).all()
+    assert lib.dinoseg_set_host_expand(m._handle, -1) == 0
+
+
+@pytest.mark.parametrize("expand", [0, 1])
+def test_async_host_submissions_match_the_synchronous_call(expand):
+    """dinoseg_predict_host_submit / _wait: several batches in flight at once (they queue behind each other on the
+    library's streams) give the bytes of one synchronous predict_batch call each, in both label-map modes (GPU
+    replication + DMA, low-res D2H + host expansion); misuse is reported, not undefined."""
+    lib = _lib.load()
+    m, cfg, sd = _model("vit_small", 2, 5, "trained_like")
+    m.set_resolution(240)
+    xs = [synthetic.make_frames(n, 240, seed=20 + n).pin_memory() for n in (5, 23, 1, 12)]
+    raw = torch.from_numpy(np.random.default_rng(3).integers(0, 256, (7, 480, 640, 3), dtype=np.uint8)).pin_memory()
+    want = [m.predict_batch(x.cuda(), output="labels").cpu().numpy() for x in xs]
+    want_raw = m.infer_u8(raw.cuda(), 240, want_logprobs=False, want_lowres=True)[1].cpu().numpy()
+    assert lib.dinoseg_set_host_expand(m._handle, expand) == 0 and lib.dinoseg_get_host_expand(m._handle) == expand
+    try:
+        for _ in range(2):                                   # second round reuses tickets, lanes and staging buffers
+            tickets = [m.predict_batch_async(x) for x in xs]                        # four submissions outstanding
+            with pytest.raises(RuntimeError, match="outstanding"):
+                m.predict_batch_async(xs[0])                                        # the fifth is refused
+            got = [m.predict_wait(t) for t in reversed(tickets)][::-1]              # waiting out of order is fine
+            for g_, w_ in zip(got, want):
+                assert g_.dtype == np.int64 and (g_ == w_).all()
+            t_raw = m.predict_batch_async(raw, resolution=240, output="lowres")
+            t_f32 = m.predict_batch_async(xs[1])
+            assert (m.predict_wait(t_f32) == want[1]).all()
+            assert (m.predict_wait(t_raw) == want_raw).all()
+            with pytest.raises(KeyError):
+                m.predict_wait(t_raw)                                               # a ticket is good for one wait
+        assert lib.dinoseg_predict_host_wait(m._handle, 12345) != 0 and "unknown ticket" in _lib.last_error(m._handle)
+        assert lib.dinoseg_predict_host_wait(m._handle, 0) == 0                     # nothing outstanding: a no-op
+    finally:
+        lib.dinoseg_set_host_expand(m._handle, -1)
 
 
 @pytest.mark.parametrize("hw,res", [((480, 640), 480), ((480, 640), 240), ((360, 500), 480), ((480, 480), 480)])
