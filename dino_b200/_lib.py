@@ -92,11 +92,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("DINOSEG_LIB", LIB_PATH)    # measurement aid: another build of the SAME library (A/B runs)
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m dino_b200.build` "
+            f"{path} is missing: build it with `python -m dino_b200.build` "
             "(there is no CPU / PyTorch fallback for the DINOSeg hot path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
