@@ -65,10 +65,16 @@ constexpr int ATT_BM = 128;     // queries per tile (two tiles per work item)
 constexpr int ATT_BN = 128;     // keys per tile
 constexpr int ATT_DH = 64;      // head dim
 constexpr int att_threads(int smw) { return 128 + 64 * smw; }   // producer warpgroup + 2 query tiles x SMW warps
-#ifndef DSG_ATTN_POLY_MASK
-#define DSG_ATTN_POLY_MASK 0x8888
+// bit i: pair i of every 16-pair chunk uses the polynomial exp2 instead of MUFU.EX2.  The best share depends on the
+// softmax form: with one row per thread (two softmax warps per scheduler) a quarter of the pairs (1.606 / 1.540 /
+// 1.512 / 1.593 ms at 0 / 12.5 / 25 / 31 %); with 16-row warps (four per scheduler) the kernel is no longer bound by
+// the exponentials alone but also by its instruction issue, and every polynomial pair costs 15 instructions against
+// 5: an eighth (1.446 / 1.397 / 1.441 / 1.520 ms at 0 / 12.5 / 25 / 37.5 %).
+#ifdef DSG_ATTN_POLY_MASK
+constexpr unsigned ATT_POLY_MASK_ROWS = DSG_ATTN_POLY_MASK, ATT_POLY_MASK_QUADS = DSG_ATTN_POLY_MASK;
+#else
+constexpr unsigned ATT_POLY_MASK_ROWS = 0x8888, ATT_POLY_MASK_QUADS = 0x8080;
 #endif
-constexpr unsigned ATT_POLY_MASK = DSG_ATTN_POLY_MASK;   // bit i: pair i of every 16-pair chunk uses the polynomial exp2
 constexpr int ATT_TILE_BYTES = 128 * ATT_DH * 2;  // 16 KB (Q, K or V tile)
 
 // Work items.  A regular item is a PAIR of 128-query tiles of one (frame, head): both warpgroups share one K/V
@@ -129,11 +135,19 @@ constexpr size_t attn_smem_bytes() {
 template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
-// TMEM columns (all 512): S_t 128 fp32 columns at t*128, P_t 64 columns (128 bf16 keys, two per column) at 256 + t*64,
-// O_t 64 fp32 columns at 384 + t*64
-constexpr uint32_t ATT_S_COL0 = 0, ATT_P_COL0 = 256, ATT_O_COL0 = 384;
+// TMEM columns (all 512): query tile t owns columns [t*256, t*256 + 256): S_t 128 fp32 columns, then P_t 64 columns (128
+// bf16 keys, two per column), then O_t 64 fp32 columns - one base address per query tile, constant offsets from it
+constexpr uint32_t ATT_T_COLS = 256, ATT_S_OFF = 0, ATT_P_OFF = 128, ATT_O_OFF = 192;
 constexpr float ATT_LOG2E = 1.4426950408889634f;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays <= 2^8
+
+// register split of the 640-thread form (see the setmaxnreg comment in the kernel): 128 * producer + 512 * softmax <= 61440
+#ifndef DSG_ATT_QUAD_SOFTMAX_REGS
+#define DSG_ATT_QUAD_SOFTMAX_REGS 104
+#define DSG_ATT_QUAD_PRODUCER_REGS 56
+#endif
+constexpr int ATT_QUAD_SOFTMAX_REGS = DSG_ATT_QUAD_SOFTMAX_REGS, ATT_QUAD_PRODUCER_REGS = DSG_ATT_QUAD_PRODUCER_REGS;
+static_assert(128 * ATT_QUAD_PRODUCER_REGS + 512 * ATT_QUAD_SOFTMAX_REGS <= 640 * 96, "register pool of the 640-thread CTA");
 
 struct AttBars {
   uint64_t *s_full, *s_empty, *p_full, *pv_done;
@@ -150,7 +164,6 @@ __device__ __forceinline__ float2 att_exp_pair(float s0, float s1, float2 l2e, f
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void att_softmax_rows(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
                                                  const int warp, const int lane, const int num_tiles) {
-  constexpr uint32_t S_COL0 = ATT_S_COL0, P_COL0 = ATT_P_COL0, O_COL0 = ATT_O_COL0;
   constexpr float LOG2E = ATT_LOG2E, RESCALE_THRESHOLD = ATT_RESCALE_THRESHOLD;
   uint64_t* const s_full = bars.s_full; uint64_t* const s_empty = bars.s_empty;
   uint64_t* const p_full = bars.p_full; uint64_t* const pv_done = bars.pv_done;
@@ -159,9 +172,9 @@ __device__ __forceinline__ void att_softmax_rows(const AttnParams& p, const uint
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
-    const uint32_t s_addr = lane_base + S_COL0 + uint32_t(t * 128);
-    const uint32_t o_addr = lane_base + O_COL0 + uint32_t(t * 64);
-    const uint32_t p_addr = lane_base + P_COL0 + uint32_t(t * 64);
+    const uint32_t s_addr = lane_base + uint32_t(t) * ATT_T_COLS + ATT_S_OFF;
+    const uint32_t o_addr = lane_base + uint32_t(t) * ATT_T_COLS + ATT_O_OFF;
+    const uint32_t p_addr = lane_base + uint32_t(t) * ATT_T_COLS + ATT_P_OFF;
     uint32_t sc = 0;                               // key tiles processed so far by this warpgroup
 #ifdef DSG_ATTN_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -248,7 +261,7 @@ __device__ __forceinline__ void att_softmax_rows(const AttnParams& p, const uint
             const float2 e = x;
 #else
             // a fixed share of the pairs is evaluated on the FMA/ALU pipes (exp2_poly_x2), the rest on MUFU
-            const float2 e = ((ATT_POLY_MASK >> i) & 1) ? exp2_poly_x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            const float2 e = ((ATT_POLY_MASK_ROWS >> i) & 1) ? exp2_poly_x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
 #endif
 #ifndef DSG_EXP_NO_SUM
             if (i & 1) sum23 = fadd2(sum23, e); else sum01 = fadd2(sum01, e);
@@ -325,11 +338,14 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
   const int t = (warp - 4) >> 3;                   // query tile of this warp
   const int rbase = (warp & 3) * 32 + (((warp - 4) >> 2) & 1) * 16;   // first of the warp's 16 rows (= TMEM lanes)
   const int qd = lane & 3;                         // this thread's rows: rbase + lane / 4 and rbase + lane / 4 + 8
-  const uint32_t lane_base = tmem_base + (uint32_t(rbase) << 16);
-  const uint32_t s_addr = lane_base + ATT_S_COL0 + uint32_t(t * 128);
-  const uint32_t p_addr = lane_base + ATT_P_COL0 + uint32_t(t * 64);
-  const uint32_t o_addr = lane_base + ATT_O_COL0 + uint32_t(t * 64);
+  // one TMEM base per warp (its 16 lanes, its query tile's columns); S / P / O are constant offsets from it
+  const uint32_t t_addr = tmem_base + (uint32_t(rbase) << 16) + uint32_t(t) * ATT_T_COLS;
+  const uint32_t s_addr = t_addr + ATT_S_OFF, p_addr = t_addr + ATT_P_OFF, o_addr = t_addr + ATT_O_OFF;
   const float2 l2e = make_float2(LOG2E, LOG2E);
+  // shared-memory address of this query tile's barriers, computed once (see mbar_wait_a): s_full[2], s_empty[2],
+  // p_full[2], pv_done[2] are consecutive, so the four barriers of tile t are constant offsets from one register
+  const uint32_t b_s_full = smem_u32(&bars.s_full[t]);
+  const uint32_t b_s_empty = b_s_full + 16, b_p_full = b_s_full + 32, b_pv_done = b_s_full + 48;
   uint32_t sc = 0;                                 // key tiles processed so far by this query tile
 
   for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -342,13 +358,13 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
     float l0 = 0.f, l1 = 0.f;                      // this thread's share of the running row sums of exp(s - m)
 
     for (int j = 0; j < num_tiles; ++j, ++sc) {
-      mbar_wait(&bars.s_full[t], sc & 1);
+      mbar_wait_a(b_s_full, sc & 1);
       tc_fence_after();
       uint32_t sr[64];
       tmem_ld_16x256b_x16(s_addr, sr);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars.s_empty[t]);               // the tensor pipe may overwrite S_t with the next scores
+      mbar_arrive_a(b_s_empty);               // the tensor pipe may overwrite S_t with the next scores
       const int kbase = j * ATT_BN;
       if (kbase + ATT_BN > p.N) {                  // last key tile of a ragged sequence: keys >= N do not exist
 #pragma unroll
@@ -378,8 +394,8 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
       uint32_t pk[32];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const float2 e0 = att_exp_pair(S(4 * k), S(4 * k + 1), l2e, nmb0, (ATT_POLY_MASK >> ((2 * k) & 15)) & 1);
-        const float2 e1 = att_exp_pair(S(4 * k + 2), S(4 * k + 3), l2e, nmb1, (ATT_POLY_MASK >> ((2 * k + 1) & 15)) & 1);
+        const float2 e0 = att_exp_pair(S(4 * k), S(4 * k + 1), l2e, nmb0, (ATT_POLY_MASK_QUADS >> ((2 * k) & 15)) & 1);
+        const float2 e1 = att_exp_pair(S(4 * k + 2), S(4 * k + 3), l2e, nmb1, (ATT_POLY_MASK_QUADS >> ((2 * k + 1) & 15)) & 1);
         sum0 = fadd2(sum0, e0);
         sum1 = fadd2(sum1, e1);
         pk[2 * k] = pack_bf16x2(e0.x, e0.y);
@@ -387,7 +403,7 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
       }
       if (j > 0) {
         // PV_t(j-1) must have retired before P_t is overwritten or O_t is rescaled
-        mbar_wait(&bars.pv_done[t], (sc - 1) & 1);
+        mbar_wait_a(b_pv_done, (sc - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, g0 || g1)) {
           const float a0 = fast_exp2((m0 - n0) * LOG2E), a1 = fast_exp2((m1 - n1) * LOG2E);   // 1 for rows that keep m
@@ -413,12 +429,12 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
       tmem_st_16x128b_x16(p_addr, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bars.p_full[t]);
+      mbar_arrive_a(b_p_full);
     }
 
     // epilogue: O / l -> bf16 -> out[b*N + q, h*64 + d].  Row sums: add the quad's four shares; the O rows are read
     // as 16x32bx2 (lane i and i+16: row i % 16, columns 0..31 / 32..63), so each thread stores 64 contiguous bytes
-    mbar_wait(&bars.pv_done[t], (sc - 1) & 1);
+    mbar_wait_a(b_pv_done, (sc - 1) & 1);
     tc_fence_after();
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -455,7 +471,6 @@ __global__ void __launch_bounds__(att_threads(SMW), 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   static_assert(SMW == 4 || SMW == 8, "softmax warps per query tile");
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t S_COL0 = ATT_S_COL0, P_COL0 = ATT_P_COL0, O_COL0 = ATT_O_COL0;
   constexpr uint32_t ATT_ARRIVALS = 32 * SMW;    // s_empty / p_full: one arrival per softmax thread of the query tile
 
   extern __shared__ uint8_t smem_raw[];
@@ -504,7 +519,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     // Registers move from the producer warpgroup to the softmax warps.  The budget is the CTA's register pool AT LAUNCH
     // (threads x the kernel's register count), not the SM's 64 K: 384 x 168 = 64512 >= 128*80 + 256*208 (SMW = 4);
     // 640 x 96 = 61440 >= 128*56 + 512*104 (SMW = 8).  A setmaxnreg.inc beyond the pool blocks forever.
-    if constexpr (SMW == 4) setmaxnreg_dec<80>(); else setmaxnreg_dec<56>();
+    if constexpr (SMW == 4) setmaxnreg_dec<80>(); else setmaxnreg_dec<ATT_QUAD_PRODUCER_REGS>();
     if (warp == 0 && elect_one()) {
       // ------------------------------ TMA producer ------------------------------
       uint32_t kvc = 0;
@@ -538,9 +553,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0);  // K^T: K-major B
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_DH, 1);  // V  : MN-major B
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + size_t(t) * ATT_TILE_BYTES));
-      const uint32_t s_tmem = tmem_base + S_COL0 + uint32_t(t * 128);
-      const uint32_t p_tmem = tmem_base + P_COL0 + uint32_t(t * 64);
-      const uint32_t o_tmem = tmem_base + O_COL0 + uint32_t(t * 64);
+      const uint32_t s_tmem = tmem_base + uint32_t(t) * ATT_T_COLS + ATT_S_OFF;
+      const uint32_t p_tmem = tmem_base + uint32_t(t) * ATT_T_COLS + ATT_P_OFF;
+      const uint32_t o_tmem = tmem_base + uint32_t(t) * ATT_T_COLS + ATT_O_OFF;
       uint32_t kvc = 0, ct = 0;           // ct: key tiles of this query tile processed so far (barrier phases)
       int it = 0;
 #ifdef DSG_ATTN_TIMING
@@ -622,7 +637,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       setmaxnreg_inc<208>();
       att_softmax_rows(p, tmem_base, ab, warp, lane, num_tiles);
     } else {
-      setmaxnreg_inc<104>();
+      setmaxnreg_inc<ATT_QUAD_SOFTMAX_REGS>();
       att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
     }
   }

@@ -527,11 +527,11 @@ struct dinoseg {
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
   int reverse_order = 1;            // GEMM / MLP kernels walk the rows last-to-first, LN / attention first-to-last
-  // CTA-pair (cta_group::2) kernels: opt-in (dinoseg_set_pair_kernels / DINOSEG_PAIR=1).  They are bit-identical to
-  // the single-CTA kernels and measured +2 % on the whole step, but two of ~90 bench processes that used them stalled
-  // without tripping the mbarrier watchdog and the cause could not be pinned down inside the round's GPU budget.
-  bool gemm_pair = false;           // qkv / patch-embed (ViT-B: fc1, fc2) GEMMs as CTA pairs
-  bool mlp_pair = false;       // ... as CTA pairs (cta_group::2), half the weights per SM
+  // CTA-pair (cta_group::2) kernels: on by default (dinoseg_set_pair_kernels / DINOSEG_PAIR=0 select the single-CTA
+  // forms).  Bit-identical results; +2 % on the ViT-S step, +5 % on ViT-B.  A device / partition without 2-CTA
+  // clusters makes the launch fail, in which case forward_impl switches to the single-CTA kernels for good.
+  bool gemm_pair = true;            // qkv / patch-embed (ViT-B: fc1, fc2) GEMMs as CTA pairs
+  bool mlp_pair = false;            // the fused MLP as CTA pairs (set in dinoseg_create when the fused kernel applies)
 
   // optional per-kernel-kind timing (cudaEvents around every launch of a forward)
   bool profile = false;
@@ -711,6 +711,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->cfg = *cfg;
   h->device = device;
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
+  h->mlp_pair = h->fused_mlp;
   if (const char* mode = getenv("DINOSEG_PAIR")) {   // CTA-pair kernels: 0.486 vs 0.494 ms (MLP), 0.188 vs 0.212 ms (qkv)
     h->gemm_pair = atoi(mode) != 0;
     h->mlp_pair = h->fused_mlp && atoi(mode) != 0;

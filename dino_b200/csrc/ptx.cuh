@@ -109,6 +109,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same on a precomputed 32-bit shared-memory address.  Inside hot loops this matters: given a pointer, the compiler
+// re-derives the barrier's shared address (aligned dynamic-smem base + offset: ~8 instructions) at every use.
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  if (mbar_try_wait_a(bar_addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar_addr, parity)) {
+    if (clock64() - t0 > DSG_WATCHDOG_CYCLES) __trap();
+  }
+}
+
 // the same with cluster-scope acquire: for barriers that receive arrivals from the peer CTA
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
