@@ -83,6 +83,11 @@ def arm_stall_watchdog(args):
 
     def fire():
         sys.stderr.write(f"bench.py: no result after {limit:.0f} s - aborting\n")
+        try:                                        # where every thread of this process is stuck
+            import faulthandler
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        except Exception:
+            pass
         sys.stderr.flush()
         if int(os.environ.get("RANK", "0")) == 0:
             print(json.dumps({"error": f"stalled: no result after {limit:.0f} s", "impl": args.impl}), flush=True)
@@ -397,23 +402,34 @@ def main():
     fps = world * B * args.steps / (ms_max / 1e3)
 
     # ---- end-to-end: pinned host frames -> public API -> host label maps ----
-    e2e = None
-    if not args.no_e2e:
-        out_host = torch.empty((B, 480 // g * g, 480 // g * g), dtype=torch.int64).pin_memory()
-        for _ in range(2):
-            model.predict_batch(frames_host, output="labels", out=out_host)
+    # A caller that streams batches keeps two submissions in flight (DINOSeg.predict_batch_async / predict_wait): the
+    # H2D copy of step k+1 overlaps the last kernels and the D2H copy of step k.  Every step still copies its own
+    # frames from pinned host memory and delivers its own int64 label maps into (alternating) pinned host buffers.
+    def e2e_loop(frames_in, resolution, outs):
+        def run(n):
+            prev = model.predict_batch_async(frames_in, resolution=resolution, output="labels", out=outs[0])
+            for i in range(1, n):
+                t = model.predict_batch_async(frames_in, resolution=resolution, output="labels", out=outs[i % 2])
+                model.predict_wait(prev)
+                prev = t
+            return model.predict_wait(prev)
+        run(3)
         D.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            out = model.predict_batch(frames_host, output="labels", out=out_host)
+        last = run(args.steps)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt_max = D.max_over_ranks(dt)
-        # what crosses PCIe device -> host per step: by default the low-res maps, which the library's host threads
-        # expand into the int64 [480,480] maps inside the same call (np.kron of the reference); with host_expand off
-        # the maps are replicated on the GPU and copied out whole
+        return D.max_over_ranks(time.perf_counter() - t0), last
+
+    e2e = e2e_u8 = None
+    if not args.no_e2e:
         from dino_b200 import _lib as _L
+        side = 480 // g * g
+        outs = [torch.empty((B, side, side), dtype=torch.int64).pin_memory() for _ in range(2)]
+        dt_max, out = e2e_loop(frames_host, None, outs)
+        # what crosses PCIe device -> host per step: the low-res maps when the library expands them into the int64
+        # [480,480] maps with its host threads inside the same call (np.kron of the reference), else the int64 maps
+        # replicated on the GPU (automatic choice by host cores per rank, dinoseg_set_host_expand)
         expand = _L.load().dinoseg_get_host_expand(model._handle) == 1
         d2h = int((B * g * g if expand else out.size * 8) * world)
         tail = ("low-res maps D2H, expanded to int64 label maps by the library's host threads"
@@ -421,28 +437,19 @@ def main():
         e2e = {"value": world * B * args.steps / dt_max, "unit": UNIT,
                "h2d_bytes_per_step": int(frames_host.numel() * 4 * world),
                "d2h_bytes_per_step": d2h, "host_label_bytes_per_step": int(out.size * 8 * world),
-               "api": "DINOSeg.predict_batch(pinned host fp32 frames) -> int64 host label maps (dinoseg_predict_host: "
-                      "H2D + forward + D2H + sync inside the timed region, pipelined over ~10-frame chunks on 3 streams; "
-                      + tail + ")"}
-    # ---- the same from RAW camera frames (uint8 640x480 RGB, as DINOSeg.predict receives them): resize + normalise on
-    # the GPU as well; informational, the contract's `e2e` is the fp32 path above ----
-    e2e_u8 = None
-    if not args.no_e2e and res == 480:
-        import numpy as np
-        raw = torch.from_numpy(np.random.default_rng(7 + rank).integers(0, 256, (B, 480, 640, 3), dtype=np.uint8)).pin_memory()
-        for _ in range(2):
-            model.predict_batch_u8(raw, res, output="labels", out=out_host)
-        D.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            model.predict_batch_u8(raw, res, output="labels", out=out_host)
-        torch.cuda.synchronize()
-        dt_max = D.max_over_ranks(time.perf_counter() - t0)
-        e2e_u8 = {"value": world * B * args.steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": int(raw.numel() * world),
-                  "d2h_bytes_per_step": d2h, "host_label_bytes_per_step": int(out_host.numel() * 8 * world),
-                  "api": "DINOSeg.predict_batch_u8(pinned host uint8 640x480 RGB frames) -> int64 host label maps "
-                         "(cv2-exact bilinear resize + normalisation fused into the patch embed on the GPU)"}
+               "api": "DINOSeg.predict_batch_async / predict_wait (pinned host fp32 frames -> int64 host label maps; "
+                      "dinoseg_predict_host_submit / _wait: H2D + forward + D2H inside the timed region, pipelined over "
+                      "~10-frame chunks on 3 streams, two steps in flight; " + tail + ")"}
+        # ---- the same from RAW camera frames (uint8 640x480 RGB, as DINOSeg.predict receives them): resize + normalise
+        # on the GPU as well; informational, the contract's `e2e` is the fp32 path above ----
+        if res == 480:
+            import numpy as np
+            raw = torch.from_numpy(np.random.default_rng(7 + rank).integers(0, 256, (B, 480, 640, 3), dtype=np.uint8)).pin_memory()
+            dt_max, _ = e2e_loop(raw, res, outs)
+            e2e_u8 = {"value": world * B * args.steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": int(raw.numel() * world),
+                      "d2h_bytes_per_step": d2h, "host_label_bytes_per_step": int(outs[0].numel() * 8 * world),
+                      "api": "DINOSeg.predict_batch_async(pinned host uint8 640x480 RGB frames) -> int64 host label maps "
+                             "(cv2-exact bilinear resize + normalisation fused into the patch embed on the GPU)"}
     t_wall2 = time.time()
     clocks = None
     if rank == 0:

@@ -1090,8 +1090,12 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       DSG_CUDA(h, launch_gemm(EPI_BIAS_F32, w.tm_qkv_a, h->tm_h1, w.tm_lin_out, w.tm_lin_out, p, sms, s)); ++n;
     }
     LaunchScope ls(h, K_HEAD_TAIL, s);
-    head_tail_kernel<true><<<tail_grid, 256, 0, s>>>(w.x, kLinPitch, nullptr, nullptr, logprobs, lr, tail_labels, batch,
-                                                     h->g, h->p_rep, h->Ntok, 0, h->cfg.n_classes);
+    if (h->cfg.n_classes <= 8)
+      head_tail_kernel<true, 8><<<tail_grid, 256, 0, s>>>(w.x, kLinPitch, nullptr, nullptr, logprobs, lr, tail_labels, batch,
+                                                          h->g, h->p_rep, h->Ntok, 0, h->cfg.n_classes);
+    else
+      head_tail_kernel<true, 16><<<tail_grid, 256, 0, s>>>(w.x, kLinPitch, nullptr, nullptr, logprobs, lr, tail_labels, batch,
+                                                           h->g, h->p_rep, h->Ntok, 0, h->cfg.n_classes);
     DSG_CUDA(h, cudaGetLastError()); ++n;
   } else {
     {
@@ -1108,8 +1112,12 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       DSG_CUDA(h, launch_gemm(EPI_RELU_F32, w.tm_h1s_a, h->tm_h2, w.tm_h2_out, w.tm_h2_out, p, sms, s)); ++n;
     }
     LaunchScope ls(h, K_HEAD_TAIL, s);
-    head_tail_kernel<false><<<tail_grid, 256, 0, s>>>(w.x, h->cfg.head_h2, h->w3, h->b3, logprobs, lr, tail_labels, batch,
-                                                      h->g, h->p_rep, h->Ntok, h->cfg.head_h2, h->cfg.n_classes);
+    if (h->cfg.n_classes <= 8)
+      head_tail_kernel<false, 8><<<tail_grid, 256, 0, s>>>(w.x, h->cfg.head_h2, h->w3, h->b3, logprobs, lr, tail_labels, batch,
+                                                           h->g, h->p_rep, h->Ntok, h->cfg.head_h2, h->cfg.n_classes);
+    else
+      head_tail_kernel<false, 16><<<tail_grid, 256, 0, s>>>(w.x, h->cfg.head_h2, h->w3, h->b3, logprobs, lr, tail_labels, batch,
+                                                            h->g, h->p_rep, h->Ntok, h->cfg.head_h2, h->cfg.n_classes);
     DSG_CUDA(h, cudaGetLastError()); ++n;
   }
   h->launches = n;

@@ -305,12 +305,13 @@ half_counts_kernel(const uint8_t* __restrict__ lowres, int32_t* __restrict__ cou
 // ---------------------------------------------------------------------------------------
 constexpr int HEAD_MAX_C = 16;
 
-// v has HEAD_MAX_C entries (C valid); fully unrolled so that v stays in registers
+// v has HEAD_MAX_C entries (C <= MAXC valid); fully unrolled so that v stays in registers
+template <int MAXC = HEAD_MAX_C>
 __device__ __forceinline__ int argmax_first(const float (&v)[HEAD_MAX_C], int C) {
   float best = v[0];
   int idx = 0;
 #pragma unroll
-  for (int c = 1; c < HEAD_MAX_C; ++c) {
+  for (int c = 1; c < MAXC; ++c) {
     const float x = v[c];
     if (c < C && ((x > best) || (x != x && best == best))) { best = x; idx = c; }
   }
@@ -332,16 +333,18 @@ __device__ __forceinline__ int argmax_first(const float (&v)[HEAD_MAX_C], int C)
 // ---------------------------------------------------------------------------------------
 constexpr int HT_MAX_H2 = 104;
 
-template <bool LINEAR>
+// MAXC: compile-time bound of the class loops (8 or 16): every class slot costs instructions whether it is used or not
+// (with MAXC = 16 and the reference's 7 classes the kernel was bound by instruction issue, not by HBM).
+template <bool LINEAR, int MAXC>
 __global__ void __launch_bounds__(256)
 head_tail_kernel(const float* __restrict__ in /*[B*Ntok, ld]*/, int ld, const float* __restrict__ w3 /*[C, H2]*/,
                  const float* __restrict__ b3 /*[C]*/, float* __restrict__ logprobs /*[B*P, C] or null*/,
                  uint8_t* __restrict__ lowres /*[B*P] or null*/, long long* __restrict__ labels /*[B, g*p, g*p] or null*/,
                  int B, int g, int p, int Ntok, int H2, int C) {
-  __shared__ float sW3[LINEAR ? 1 : HEAD_MAX_C * HT_MAX_H2];
+  __shared__ float sW3[LINEAR ? 1 : MAXC * HT_MAX_H2];
   __shared__ float sB3[HEAD_MAX_C];
   if constexpr (!LINEAR) {
-    for (int i = threadIdx.x; i < HEAD_MAX_C * HT_MAX_H2; i += blockDim.x) {
+    for (int i = threadIdx.x; i < MAXC * HT_MAX_H2; i += blockDim.x) {
       const int c = i / HT_MAX_H2, k = i - c * HT_MAX_H2;
       sW3[i] = (c < C && k < H2) ? w3[c * H2 + k] : 0.f;
     }
@@ -365,13 +368,13 @@ head_tail_kernel(const float* __restrict__ in /*[B*Ntok, ld]*/, int ld, const fl
     for (int c = 0; c < HEAD_MAX_C; ++c) z[c] = 0.f;
     if constexpr (LINEAR) {
 #pragma unroll
-      for (int c = 0; c < HEAD_MAX_C; ++c)
+      for (int c = 0; c < MAXC; ++c)
         if (c < C) z[c] = __ldg(src + c);
     } else {
       for (int k4 = sub; k4 < H2 / 4; k4 += 8) {
         const float4 hv = __ldg(reinterpret_cast<const float4*>(src) + k4);
 #pragma unroll
-        for (int c = 0; c < HEAD_MAX_C; ++c) {
+        for (int c = 0; c < MAXC; ++c) {
           if (c < C) {
             const float* wr = sW3 + c * HT_MAX_H2 + 4 * k4;
             z[c] = fmaf(hv.x, wr[0], z[c]); z[c] = fmaf(hv.y, wr[1], z[c]);
@@ -380,7 +383,7 @@ head_tail_kernel(const float* __restrict__ in /*[B*Ntok, ld]*/, int ld, const fl
         }
       }
 #pragma unroll
-      for (int c = 0; c < HEAD_MAX_C; ++c) {
+      for (int c = 0; c < MAXC; ++c) {
         if (c < C) {
           z[c] += __shfl_xor_sync(0xffffffffu, z[c], 1);
           z[c] += __shfl_xor_sync(0xffffffffu, z[c], 2);
@@ -391,23 +394,23 @@ head_tail_kernel(const float* __restrict__ in /*[B*Ntok, ld]*/, int ld, const fl
     }
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c)
+    for (int c = 0; c < MAXC; ++c)
       if (c < C) mx = fmaxf(mx, z[c]);
     float se = 0.f;
 #pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c)
+    for (int c = 0; c < MAXC; ++c)
       if (c < C) se += expf(z[c] - mx);
     const float lse = logf(se);
 #pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c)
+    for (int c = 0; c < MAXC; ++c)
       if (c < C) z[c] = (z[c] - mx) - lse;
     if (!live) continue;
     if (logprobs != nullptr) {
 #pragma unroll
-      for (int c = 0; c < HEAD_MAX_C; ++c)
+      for (int c = 0; c < MAXC; ++c)
         if (c < C && (c & 7) == sub) logprobs[size_t(r) * C + c] = z[c];
     }
-    const int label = argmax_first(z, C);
+    const int label = argmax_first<MAXC>(z, C);
     if (lowres != nullptr && sub == 0) lowres[r] = uint8_t(label);
     if (labels != nullptr) {
       const int i = t / g, j = t - i * g;

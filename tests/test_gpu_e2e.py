@@ -304,6 +304,33 @@ def test_host_entry_point_matches_device_path():
     assert lib.dinoseg_set_host_expand(m._handle, -1) == 0
 
 
+def test_folder_inference_matches_predict(tmp_path):
+    """dt_segmentation/visualize.py-style folder inference (batched, pipelined) returns for every image exactly the map
+    DINOSeg.predict(image) returns (reference visualize.py:36-54 calls predict once per image)."""
+    from PIL import Image
+    from dino_b200 import folder
+    m, cfg, sd = _model("vit_small", 1, 7, "trained_like")
+    m.set_resolution(240)
+    sizes = [(480, 640)] * 5 + [(360, 500)] * 2 + [(480, 640)]
+    for k, hw in enumerate(sizes):
+        img = synthetic.make_image_u8(hw[0], hw[1], seed=50 + k)
+        Image.fromarray(img).save(tmp_path / f"f{k:02d}.png")
+    got = list(folder.predict_folder(m, str(tmp_path), batch_size=3))
+    assert len(got) == len(sizes)
+    assert [os.path.basename(p) for p, _, _ in got] == [os.path.basename(f) for f in folder.list_images(str(tmp_path))]
+    for path, rgb, pred in got:
+        want = m.predict(Image.open(path).convert("RGB"))
+        assert pred.shape == (480, 480) and pred.dtype == np.int64 and (pred == want).all(), path
+    # the drop-in script writes one overlay per image
+    import dt_segmentation.visualize as V
+    ck = tmp_path / "m.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": dict(head="mlp", n_blocks=1, n_classes=7)}, ck)
+    assert V.inference(str(ck), str(tmp_path), str(tmp_path / "out"), resolution=240, batch_size=4) == len(sizes)
+    assert sorted(os.listdir(tmp_path / "out")) == sorted(os.path.basename(p) for p, _, _ in got)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        V.inference(str(ck), str(tmp_path), str(tmp_path / "out2"), cpu=True)
+
+
 @pytest.mark.parametrize("expand", [0, 1])
 def test_async_host_submissions_match_the_synchronous_call(expand):
     """dinoseg_predict_host_submit / _wait: several batches in flight at once (they queue behind each other on the

@@ -338,6 +338,54 @@ def test_bench_reads_the_attention_traffic_from_profiles():
     assert src is not None and src.startswith("profiles/") and 5e8 < traffic < 1e9, (traffic, src)
 
 
+def test_folder_inference_host_logic(tmp_path):
+    """dino_b200.folder: the reference's traversal order (visualize.py:36-37: *.jpg then *.png), batches of consecutive
+    equal-size frames, results in input order with two batches in flight, and the overlay renderer."""
+    from PIL import Image
+    from dino_b200 import folder
+    rng = np.random.default_rng(0)
+    names = ["b.png", "a.jpg", "c.jpg", "d.png", "notes.txt"]
+    for n in names[:-1]:
+        Image.fromarray(rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)).save(tmp_path / n)
+    (tmp_path / names[-1]).write_text("x")
+    files = folder.list_images(str(tmp_path))
+    assert [os.path.splitext(f)[1] for f in files] == [".jpg", ".jpg", ".png", ".png"]
+    assert folder.plan_batches([(4, 4)] * 5 + [(2, 2)] + [(4, 4)] * 2, 3) == [[0, 1, 2], [3, 4], [5], [6, 7]]
+
+    class FakeModel:                                  # records the batches, answers with the frame's mean colour class
+        resolution = 480
+
+        def __init__(self):
+            self.batches, self.results, self.max_in_flight = [], {}, 0
+
+        def predict_batch_async(self, frames, resolution=None, output="labels"):
+            assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+            t = len(self.batches) + 1
+            self.batches.append(tuple(frames.shape))
+            self.results[t] = np.stack([np.full((4, 4), int(f.float().mean()) % 7, dtype=np.int64) for f in frames])
+            self.max_in_flight = max(self.max_in_flight, len(self.results))
+            return t
+
+        def predict_wait(self, t):
+            return self.results.pop(t)
+
+    imgs = [np.full((8, 8, 3), v, dtype=np.uint8) for v in (10, 20, 30, 40, 50)] + [np.full((6, 8, 3), 60, dtype=np.uint8)] + \
+           [np.full((8, 8, 3), 70, dtype=np.uint8)]
+    fm = FakeModel()
+    out = list(folder.predict_images(fm, iter(imgs), batch_size=2))
+    assert [int(o[0, 0]) for o in out] == [v % 7 for v in (10, 20, 30, 40, 50, 60, 70)]     # input order
+    assert fm.batches == [(2, 8, 8, 3), (2, 8, 8, 3), (1, 8, 8, 3), (1, 6, 8, 3), (1, 8, 8, 3)]
+    assert fm.max_in_flight == 2
+    with pytest.raises(ValueError):
+        list(folder.predict_images(fm, [np.zeros((8, 8), dtype=np.uint8)]))
+    pred = np.zeros((480, 480), dtype=np.int64)
+    pred[:100] = 3
+    ov = folder.overlay(pred, imgs[0].repeat(10, axis=0).repeat(10, axis=1))
+    assert ov.shape == (480, 480, 3) and ov.dtype == np.uint8
+    assert (ov[200:] == 10).all() and not (ov[:100] == 10).all()                               # class 0 keeps the grey image
+    assert folder.label_colormap()[:4].tolist() == [[0, 0, 0], [128, 0, 0], [0, 128, 0], [128, 128, 0]]
+
+
 def test_product_code_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under dino_b200/ or dt_segmentation/ may use it."""
     for pkg in ("dino_b200", "dt_segmentation"):
