@@ -526,6 +526,7 @@ struct dinoseg {
   int debug_stop = 0;
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
+  bool fuse_ln = true;              // ... which also computes LayerNorm2 itself (no LN launch, no bf16 copy of the tokens)
   int reverse_order = 1;            // GEMM / MLP kernels walk the rows last-to-first, LN / attention first-to-last
   // CTA-pair (cta_group::2) kernels: on by default (dinoseg_set_pair_kernels / DINOSEG_PAIR=0 select the single-CTA
   // forms).  Bit-identical results; +2 % on the ViT-S step, +5 % on ViT-B.  A device / partition without 2-CTA
@@ -718,6 +719,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   }
   if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0 ? 1 : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
+  if (const char* mode = getenv("DINOSEG_FUSE_LN")) h->fuse_ln = atoi(mode) != 0;         // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
     const int m = atoi(mode);
@@ -1031,11 +1033,18 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     }
     if (stop == 3 + 3 * i) { h->launches = n; return 0; }
     if (h->fused_mlp) {
-      // LayerNorm2, then fc1 -> GELU -> fc2 -> +x in ONE kernel (ViT-S: D = 384, hidden = 1536)
-      { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n; }
+      // LayerNorm2 -> fc1 -> GELU -> fc2 -> +x in ONE kernel (ViT-S: D = 384, hidden = 1536); with fuse_ln off the
+      // LayerNorm runs as its own kernel and the MLP kernel TMA-loads its bf16 output
       MlpParams p{};
       p.M = M; p.x = w.x; p.b1 = b.fc1_b; p.b2 = b.fc2_b;
-      p.reverse = h->reverse_order;              // LN2 wrote abuf first-to-last
+      if (h->fuse_ln) {
+        p.ln_g = b.ln2_g; p.ln_b = b.ln2_b; p.ln_eps = eps;
+      } else {
+        LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n;
+      }
+      // start with the rows the producer of x / A wrote last: LN2 writes first-to-last (-> walk backwards), the proj GEMM
+      // walks backwards itself (-> walk forwards when the LayerNorm is fused and this kernel follows it directly)
+      p.reverse = h->fuse_ln ? (h->reverse_order ? 0 : 1) : h->reverse_order;
       LaunchScope ls(h, K_MLP_FUSED, s);
       if (h->mlp_pair && launch_mlp_fused(w.tm_abuf, b.tm_fc1_h, b.tm_fc2_h, w.tm_x_out, p, sms, true, s) != cudaSuccess) {
         (void)cudaGetLastError();   // no 2-CTA clusters on this device / partition: same kernel, one CTA per row block
@@ -1623,6 +1632,25 @@ int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const f
   MlpParams p{};
   p.M = M; p.x = x; p.b1 = b1; p.b2 = b2;
   return launch_mlp_fused(ta, t1, t2, tx, p, sms, pair != 0, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_op_mlp_ln(float* x, const float* gamma, const float* beta, float eps, const void* W1_bf16, const float* b1,
+                      const void* W2_bf16, const float* b2, int M, int pair, void* stream) {
+  if (!x || !gamma || !beta || !W1_bf16 || !b1 || !W2_bf16 || !b2 || M <= 0) return -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap t1, t2, tx;
+  const uint32_t wrows = pair ? 64 : 128;
+  bool ok = make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, wrows);
+  ok &= make_tmap_2d(&t2, W2_bf16, MLP_D, MLP_HID, MLP_HID, wrows);
+  ok &= make_tmap_gemm_out(&tx, x, true, MLP_D, M, 1, MLP_D);
+  if (!ok) return -2;
+  MlpParams p{};
+  p.M = M; p.x = x; p.b1 = b1; p.b2 = b2;
+  p.ln_g = gamma; p.ln_b = beta; p.ln_eps = eps;
+  // (the A tensor map is not used by the fused-LayerNorm form; tx stands in for it)
+  return launch_mlp_fused(tx, t1, t2, tx, p, sms, pair != 0, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* stream) {

@@ -5,9 +5,12 @@
 // leaves the SM (the unfused path writes and re-reads 708 MB of it per block at batch 64), and the
 // hidden bias / GELU / residual passes are fused:
 //
-//   A block     : LayerNorm2(x) as bf16 (written by the LayerNorm kernel) is TMA-loaded once per row block and
-//                 stays resident in shared memory (6 k-blocks x 16 KB); the next block's A is requested as soon
-//                 as the last MMA1 of the current block has been issued
+//   A block     : LayerNorm2(x) as bf16, resident in shared memory (6 k-blocks x 16 KB) for the 12 hidden chunks of a row
+//                 block.  Fused form (MlpParams::ln_g): the four output warps - idle between two drains - read the
+//                 block's 128 rows of x (fp32, prefetched into L2 one block ahead), normalise them exactly as the
+//                 LayerNorm kernel does and write the bf16 operand in the UMMA layout as soon as the last MMA1 of
+//                 the previous block has retired: no LayerNorm launch, no bf16 copy of the tokens in HBM.
+//                 Unfused form: the block is TMA-loaded from the bf16 copy the LayerNorm kernel wrote.
 //   per hidden chunk c of 128 columns (12 chunks):
 //     MMA1(c)   : acc1[128 x 128] = A . W1[c]^T              (24 MMAs 128x128x16, W1 granules via TMA)
 //     GELU warps: acc1 -> registers -> + b1 -> GELU -> bf16 -> shared memory G (again an A-operand layout)
@@ -29,10 +32,15 @@ namespace dsg {
 
 struct MlpParams {
   int M;                      // token rows
-  const float* x;             // [M, 384] fp32 residual stream (read by the output warps; written through tmX)
+  const float* x;             // [M, 384] fp32 residual stream (read by the LayerNorm fill; written through tmX)
   const float* b1;            // [1536]
   const float* b2;            // [384]
   int reverse;                // 1: row blocks are processed last to first
+  // fused LayerNorm2 (reference vision_transformer.py:118, :135): when ln_g != nullptr the A block is not TMA-loaded
+  // from a bf16 copy written by the LayerNorm kernel but produced in place from x by the output warps
+  const float* ln_g;          // [384] or nullptr
+  const float* ln_b;          // [384]
+  float ln_eps;
   long long* timing;          // debug (DSG_MLP_TIMING): [grid][2 roles][8] cycle totals
 };
 
@@ -155,7 +163,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < RING; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a_full, 1);
+    mbar_init(a_full, p.ln_g != nullptr ? 4 * NCTA : 1);   // fused LayerNorm: one arrival per output warp (both CTAs)
     mbar_init(a_empty, 1);
     mbar_init(acc1_full, 1);
     mbar_init(acc1_empty, 8 * NCTA);
@@ -229,12 +237,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < MLP_KB; ++kb) tma_load_3d(sA + size_t(kb) * MLP_GRAN, &tmA, a_full, kb * 64, r0, 0);
         }
       };
-      if (my_blocks > 0) load_a(0);
+      const bool tma_a = p.ln_g == nullptr;      // fused LayerNorm: the output warps produce A
+      if (my_blocks > 0 && tma_a) load_a(0);
       for (int bi = 0; bi < my_blocks; ++bi) {
         for (int i = 0; i < MLP_NCH + MLP_LAG; ++i) {
           if (i < MLP_NCH) load_w1(i);
           // the A block of the next row block: right after the weights of the last MMA1 have been requested
-          if (i == MLP_NCH - 1 && bi + 1 < my_blocks) load_a(bi + 1);
+          if (i == MLP_NCH - 1 && bi + 1 < my_blocks && tma_a) load_a(bi + 1);
           if (i >= MLP_LAG) load_w2(i - MLP_LAG);
         }
       }
@@ -245,7 +254,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t idx = rc - 1 - i;
           mbar_wait(&w_empty[idx % RING], (idx / RING) & 1);
         }
-        if (my_blocks > 0) mbar_wait(a_empty, (my_blocks - 1) & 1);
+        if (my_blocks > 0 && tma_a) mbar_wait(a_empty, (my_blocks - 1) & 1);   // (fused: the output warps wait for it)
       }
     }
   } else if (warp == 1) {
@@ -441,8 +450,89 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
     constexpr int NCH = MLP_D / 32;                 // 12
     uint32_t addc = 0;                              // staging chunks so far
+    // ---- fused LayerNorm2: A block of row block bi from x ----
+    // Warp w of the four takes rows w*32 .. w*32+31, four rows at a time; a row is read as three float4 per lane
+    // (columns i*128 + lane*4 ..+3, the access pattern and the arithmetic of layernorm_bf16_kernel: two-pass statistics
+    // in registers, xor-shuffle sums), normalised, rounded to bf16 and written into the k-block slots of sA in the
+    // K-major SWIZZLE_128B layout the TMA load would have produced: column c of row r -> slot c/64, byte
+    // r*128 + (((c%64)/8 ^ (r&7)) << 4) + (c%8)*2.  Rows >= M are written as zeros (what TMA's fill does).
+    const bool fuse_ln = p.ln_g != nullptr;
+    const int ow = warp - 10;                       // 0..3
+    float4 gm[3], bt[3];
+    if (fuse_ln) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        gm[i] = __ldg(reinterpret_cast<const float4*>(p.ln_g) + i * 32 + lane);
+        bt[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i * 32 + lane);
+      }
+    }
+    auto prefetch_block = [&](int bi) {             // the block's 128 rows of x -> L2 (192 KB: 12 lines per thread)
+      const int r0 = block_row0(bi);
+      const char* base = reinterpret_cast<const char*>(p.x + size_t(r0) * MLP_D);
+      const size_t bytes = size_t(max(0, min(MLP_BM, p.M - r0))) * MLP_D * sizeof(float);
+      for (size_t off = size_t(threadIdx.x - 320) * 128; off < bytes; off += 128 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    };
+    auto ln_fill = [&](int bi) {
+      const int r0 = block_row0(bi);
+      if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1); // the last MMA1 of the previous block has read A
+      for (int rb = 0; rb < 32; rb += 4) {
+        float4 v[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = r0 + ow * 32 + rb + q;
+          const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(row) * MLP_D);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) v[q][i] = row < p.M ? __ldg(xr + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = ow * 32 + rb + q;           // row inside the block
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sum += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float mean = sum * (1.0f / MLP_D);
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
+            sq += (a * a + b * b) + (c * c + d * d);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          const float rstd = rsqrtf(sq * (1.0f / MLP_D) + p.ln_eps);
+          const bool live = r0 + r < p.M;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float a = (v[q][i].x - mean) * rstd * gm[i].x + bt[i].x, b = (v[q][i].y - mean) * rstd * gm[i].y + bt[i].y;
+            const float c = (v[q][i].z - mean) * rstd * gm[i].z + bt[i].z, d = (v[q][i].w - mean) * rstd * gm[i].w + bt[i].w;
+            uint2 o;
+            o.x = live ? pack_bf16x2(a, b) : 0u;
+            o.y = live ? pack_bf16x2(c, d) : 0u;
+            // columns i*128 + lane*4 .. +3: k-block 2i + lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
+            uint8_t* dst = sA + size_t(2 * i + (lane >> 4)) * MLP_GRAN + r * 128 + ((((lane & 15) >> 1) ^ (r & 7)) << 4) +
+                           (lane & 1) * 8;
+            *reinterpret_cast<uint2*>(dst) = o;
+          }
+        }
+      }
+      fence_proxy_async_smem();                     // generic-proxy writes -> visible to the UMMA reads of sA
+      __syncwarp();
+      if (lane == 0) arrive_leader(a_full);
+    };
+    if (fuse_ln && my_blocks > 0) {
+      ln_fill(0);
+      if (my_blocks > 1) prefetch_block(1);
+    }
     for (int bi = 0; bi < my_blocks; ++bi) {
       const int r0 = block_row0(bi);
+      if (fuse_ln && bi + 1 < my_blocks) {
+        // the next block's A: as soon as this block's last MMA1 has retired (a_empty), i.e. while its last MMA2s run
+        ln_fill(bi + 1);
+        if (bi + 2 < my_blocks) prefetch_block(bi + 2);
+      }
       mbar_wait(acc2_full, bi & 1);                 // every MMA2 of this block has retired
       tc_fence_after();
       for (int ch = 0; ch < NCH; ++ch, ++addc) {
@@ -479,6 +569,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
+    }
+    if constexpr (PAIR) {
+      if (fuse_ln && my_blocks > 0) mbar_wait(a_empty, (my_blocks - 1) & 1);   // producer tail (see the TMA producer)
     }
     if (leader) tma_store_wait<0>();
   }

@@ -195,6 +195,10 @@ int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const floa
 /* the same kernel run by CTA pairs (tcgen05 cta_group::2, M = 256 per MMA, weights split between the two SMs) when pair != 0 */
 int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                       const float* b2, int M, int pair, void* stream);
+/* x[M,384] fp32 (in place) += fc2(gelu(fc1(LayerNorm(x; gamma, beta, eps)))): the fused MLP kernel in the form the
+ * forward uses, computing LayerNorm2 itself from the fp32 residual stream (vision_transformer.py:118, :135) */
+int dinoseg_op_mlp_ln(float* x, const float* gamma, const float* beta, float eps, const void* W1_bf16, const float* b1,
+                      const void* W2_bf16, const float* b2, int M, int pair, void* stream);
 /* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel, one CTA per row block; 2: fused MLP kernel run by CTA pairs
  * (cta_group::2); 2 is the default where the fused kernel applies (embed_dim 384, mlp_hidden 1536) */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);

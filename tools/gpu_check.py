@@ -184,6 +184,39 @@ def check_mlp(name, M, pair=0):
                    ref_absmax=scale, tol=tol, n_bad=int(bad.shape[0]), first_bad=bad[0].tolist() if bad.numel() else None)
 
 
+def check_mlp_ln(name, M, pair=0):
+    """The fused MLP kernel computing LayerNorm2 itself (dinoseg_op_mlp_ln) must reproduce, BIT FOR BIT, the LayerNorm
+    kernel followed by the same MLP kernel on its bf16 output (same arithmetic, same operand bytes), and match fp32 torch."""
+    torch, L, lib = _imports()
+    torch.manual_seed(8)
+    dev = "cuda"
+    x = torch.randn(M, 384, device=dev) * 1.5 + 0.2
+    x[3] *= 40.0                                   # a row with a large mean / spread
+    g = 1.0 + 0.1 * torch.randn(384, device=dev)
+    b = 0.1 * torch.randn(384, device=dev)
+    W1 = (torch.randn(1536, 384, device=dev) * 0.05).to(torch.bfloat16)
+    b1 = 0.1 * torch.randn(1536, device=dev)
+    W2 = (torch.randn(384, 1536, device=dev) * 0.03).to(torch.bfloat16)
+    b2 = 0.1 * torch.randn(384, device=dev)
+    F = torch.nn.functional
+    ln = F.layer_norm(x, (384,), g, b, 1e-6)
+    hid = F.gelu(F.linear(ln.to(torch.bfloat16).float(), W1.float(), b1))
+    ref = x + F.linear(hid.to(torch.bfloat16).float(), W2.float(), b2)
+    A = torch.zeros(M, 384, device=dev, dtype=torch.bfloat16)
+    rc0 = lib.dinoseg_op_layernorm(_ptr(x), _ptr(g), _ptr(b), _ptr(A), M, 384, 1e-6, None)
+    two = x.clone()
+    rc1 = lib.dinoseg_op_mlp_ex(_ptr(two), _ptr(A), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, pair, None)
+    one = x.clone()
+    rc2 = lib.dinoseg_op_mlp_ln(_ptr(one), _ptr(g), _ptr(b), 1e-6, _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, pair, None)
+    torch.cuda.synchronize()
+    err = (one - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    same = bool(torch.equal(one, two))
+    return _report(name, rc0 == 0 and rc1 == 0 and rc2 == 0 and same and err <= 1e-2 * scale and bool(torch.isfinite(one).all()),
+                   rc=[rc0, rc1, rc2], identical_to_ln_kernel_plus_mlp=same, max_abs_err=err, ref_absmax=scale,
+                   max_diff_vs_two_kernels=(one - two).abs().max().item())
+
+
 def check_layernorm(name, M, D):
     torch, L, lib = _imports()
     torch.manual_seed(3)
@@ -296,6 +329,10 @@ def _checks():
         "mlp_pair_1block": lambda: check_mlp("mlp_pair_1block", 128, 1),
         "mlp_pair_ragged": lambda: check_mlp("mlp_pair_ragged", 901, 1),
         "mlp_pair_multi": lambda: check_mlp("mlp_pair_multi", 148 * 128 * 2 + 77, 1),
+        "mlp_ln_ragged": lambda: check_mlp_ln("mlp_ln_ragged", 901),
+        "mlp_ln_multi": lambda: check_mlp_ln("mlp_ln_multi", 148 * 128 * 2 + 77),
+        "mlp_ln_pair_ragged": lambda: check_mlp_ln("mlp_ln_pair_ragged", 901, 1),
+        "mlp_ln_pair_multi": lambda: check_mlp_ln("mlp_ln_pair_multi", 148 * 128 * 3 + 300, 1),
     }
 
 
@@ -305,6 +342,7 @@ def check_names():
         "argmax_replicate", "argmax_replicate_odd", "gemm_tile", "gemm_k384", "gemm_qkv", "gemm_pair_small", "gemm_pair_qkv", "gemm_pair_big", "gemm_pair_vitb", "gemm_pair_gelu", "gemm_pair_resid", "gemm_gelu",
         "gemm_resid_k1536", "gemm_patch", "gemm_head", "gemm_big", "attn_1tile", "attn_ragged_small", "attn_2tiles",
         "attn_901", "attn_3601", "attn_vitb_901", "mlp_1block", "mlp_ragged", "mlp_multi", "mlp_pair_1block", "mlp_pair_ragged", "mlp_pair_multi",
+        "mlp_ln_ragged", "mlp_ln_multi", "mlp_ln_pair_ragged", "mlp_ln_pair_multi",
     ]
 
 
