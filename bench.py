@@ -75,6 +75,10 @@ def parse_args():
     return args
 
 
+PHASE = ["start"]          # where the run is (reported by the stall watchdog)
+STALL_HOOKS = []           # callables returning a diagnostic string
+
+
 def arm_stall_watchdog(args):
     """A stalled run (GPU kernel that never returns, wedged collective, ...) must END: after the limit the process
     prints an error line and exits hard (os._exit tears the CUDA context down, which kills whatever is running)."""
@@ -82,7 +86,12 @@ def arm_stall_watchdog(args):
     limit = args.stall_limit if args.stall_limit > 0 else 300.0 + 2.0 * (args.steps + args.warmup)
 
     def fire():
-        sys.stderr.write(f"bench.py: no result after {limit:.0f} s - aborting\n")
+        sys.stderr.write(f"bench.py: no result after {limit:.0f} s - aborting (phase: {PHASE[0]})\n")
+        for hook in STALL_HOOKS:                    # what the GPU side says (registered once the model exists)
+            try:
+                sys.stderr.write(hook() + "\n")
+            except Exception as e:                  # noqa: BLE001 - diagnostics must not mask the stall report
+                sys.stderr.write(f"stall hook failed: {e}\n")
         try:                                        # where every thread of this process is stuck
             import faulthandler
             faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
@@ -90,7 +99,8 @@ def arm_stall_watchdog(args):
             pass
         sys.stderr.flush()
         if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps({"error": f"stalled: no result after {limit:.0f} s", "impl": args.impl}), flush=True)
+            print(json.dumps({"error": f"stalled: no result after {limit:.0f} s", "impl": args.impl, "phase": PHASE[0]}),
+                  flush=True)
         os._exit(3)
 
     t = threading.Timer(limit, fire)
@@ -372,6 +382,19 @@ def main():
     def step():
         return model.infer(frames, want_logprobs=False, want_labels=True)[2]
 
+    def gpu_state():
+        import ctypes as C
+        from dino_b200 import _lib as _L
+        slot = C.c_int(-1)
+        kind = _L.load().dinoseg_debug_pending_kind(model._handle, C.byref(slot))
+        name = _L.load().dinoseg_profile_kind_name(kind).decode() if kind >= 0 else str(kind)
+        smi = subprocess.run(["nvidia-smi", "--query-gpu=utilization.gpu,clocks.sm,power.draw,memory.used",
+                              "--format=csv,noheader", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout.strip()
+        return f"pending launch: kind {name} (slot {slot.value}); nvidia-smi: {smi}"
+
+    STALL_HOOKS.append(gpu_state)
+    PHASE[0] = "warm-up"
+
     for _ in range(max(3, args.warmup)):
         labels = step()
     torch.cuda.synchronize()
@@ -383,7 +406,9 @@ def main():
         time.sleep(0.3)
 
     # ---- timed region: device-resident inputs; events on the launching stream ----
-    model.profile_enable(True, kinds=("attention",))        # events around the dominant kernel only
+    PHASE[0] = "timed region (device-resident frames)"
+    # events around the dominant kernel only (DINOSEG_BENCH_ALL_EVENTS=1: around every launch, for stall diagnosis)
+    model.profile_enable(True, kinds=None if os.environ.get("DINOSEG_BENCH_ALL_EVENTS") == "1" else ("attention",))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     D.barrier()
     torch.cuda.synchronize()
@@ -422,6 +447,7 @@ def main():
         return D.max_over_ranks(time.perf_counter() - t0), last
 
     e2e = e2e_u8 = None
+    PHASE[0] = "e2e (host frames, pipelined)"
     if not args.no_e2e:
         from dino_b200 import _lib as _L
         side = 480 // g * g
@@ -458,6 +484,7 @@ def main():
 
     # ---- per-kernel breakdown (optional, separate profiled pass; not part of `value`) ----
     kinds = None
+    PHASE[0] = "per-kernel breakdown"
     if args.kernels:
         model.profile_enable(True)
         for _ in range(3):

@@ -925,6 +925,24 @@ int dinoseg_profile_set_mask(dinoseg_t* h, uint32_t kind_mask) {
   return 0;
 }
 
+// Diagnostic for a forward that does not finish (callable from another host thread while the launching thread is
+// blocked in a synchronise): the kind of the first profiled launch whose start event has completed and whose end event
+// has not, -1 if there is none, -2 without profiling.  slot_out (optional) receives the launch index.
+int dinoseg_debug_pending_kind(dinoseg_t* h, int* slot_out) {
+  if (!h) return -2;
+  if (!h->profile || h->ev_used == 0) return -2;
+  const int n = h->ev_used;
+  for (int i = 0; i < n && 2 * i + 1 < int(h->ev.size()); ++i) {
+    const cudaError_t a = cudaEventQuery(h->ev[2 * i]), b = cudaEventQuery(h->ev[2 * i + 1]);
+    if (b == cudaSuccess) continue;
+    if (slot_out) *slot_out = i;
+    (void)cudaGetLastError();
+    return a == cudaSuccess ? h->ev_kind[i] : -3;   // -3: even the start event is pending (an EARLIER, unprofiled launch is stuck)
+  }
+  (void)cudaGetLastError();
+  return -1;
+}
+
 int dinoseg_profile_num_kinds(void) { return K_COUNT; }
 const char* dinoseg_profile_kind_name(int kind) { return (kind >= 0 && kind < K_COUNT) ? kKindNames[kind] : ""; }
 
