@@ -385,12 +385,14 @@ def main():
     def gpu_state():
         import ctypes as C
         from dino_b200 import _lib as _L
-        slot = C.c_int(-1)
-        kind = _L.load().dinoseg_debug_pending_kind(model._handle, C.byref(slot))
-        name = _L.load().dinoseg_profile_kind_name(kind).decode() if kind >= 0 else str(kind)
+        lib = _L.load()
+        kinds, slots, waiting = (C.c_int * 8)(), (C.c_int * 8)(), C.c_int(0)
+        n = lib.dinoseg_debug_pending_kinds(model._handle, kinds, slots, 8, C.byref(waiting))
+        running = [f"{lib.dinoseg_profile_kind_name(kinds[i]).decode()}#{slots[i]}" for i in range(max(n, 0))]
         smi = subprocess.run(["nvidia-smi", "--query-gpu=utilization.gpu,clocks.sm,power.draw,memory.used",
                               "--format=csv,noheader", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout.strip()
-        return f"pending launch: kind {name} (slot {slot.value}); nvidia-smi: {smi}"
+        return (f"launches started and not finished: {running if n >= 0 else 'profiling off'}; queued behind them: "
+                f"{waiting.value}; nvidia-smi: {smi}")
 
     STALL_HOOKS.append(gpu_state)
     PHASE[0] = "warm-up"
@@ -448,6 +450,8 @@ def main():
 
     e2e = e2e_u8 = None
     PHASE[0] = "e2e (host frames, pipelined)"
+    if os.environ.get("DINOSEG_BENCH_ALL_EVENTS") == "1":
+        model.profile_enable(True)                 # stall diagnosis: events around every launch of the host path too
     if not args.no_e2e:
         from dino_b200 import _lib as _L
         side = 480 // g * g

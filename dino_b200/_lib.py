@@ -52,7 +52,7 @@ SIGNATURES = {
     "dinoseg_last_launch_count": (C.c_int, [C.c_void_p]),
     "dinoseg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_profile_set_mask": (C.c_int, [C.c_void_p, C.c_uint32]),
-    "dinoseg_debug_pending_kind": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "dinoseg_debug_pending_kinds": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "dinoseg_profile_num_kinds": (C.c_int, []),
     "dinoseg_profile_kind_name": (C.c_char_p, [C.c_int]),
     "dinoseg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),

@@ -925,22 +925,25 @@ int dinoseg_profile_set_mask(dinoseg_t* h, uint32_t kind_mask) {
   return 0;
 }
 
-// Diagnostic for a forward that does not finish (callable from another host thread while the launching thread is
-// blocked in a synchronise): the kind of the first profiled launch whose start event has completed and whose end event
-// has not, -1 if there is none, -2 without profiling.  slot_out (optional) receives the launch index.
-int dinoseg_debug_pending_kind(dinoseg_t* h, int* slot_out) {
-  if (!h) return -2;
+// Diagnostic for work that does not finish (callable from another host thread while the launching thread is blocked
+// in a synchronise): the profiled launches whose start event has completed and whose end event has not - the kernels
+// that are running (or stuck) right now, one per stream at most.  Returns how many were written to kinds[] / slots[]
+// (up to max_out); -2 without profiling.  *not_started (optional): launches whose start event is pending as well.
+int dinoseg_debug_pending_kinds(dinoseg_t* h, int* kinds, int* slots, int max_out, int* not_started) {
+  if (!h || !kinds || !slots || max_out < 1) return -2;
   if (!h->profile || h->ev_used == 0) return -2;
-  const int n = h->ev_used;
-  for (int i = 0; i < n && 2 * i + 1 < int(h->ev.size()); ++i) {
-    const cudaError_t a = cudaEventQuery(h->ev[2 * i]), b = cudaEventQuery(h->ev[2 * i + 1]);
-    if (b == cudaSuccess) continue;
-    if (slot_out) *slot_out = i;
-    (void)cudaGetLastError();
-    return a == cudaSuccess ? h->ev_kind[i] : -3;   // -3: even the start event is pending (an EARLIER, unprofiled launch is stuck)
+  int n_out = 0, waiting = 0;
+  for (int i = 0; i < h->ev_used && 2 * i + 1 < int(h->ev.size()); ++i) {
+    if (cudaEventQuery(h->ev[2 * i + 1]) == cudaSuccess) continue;
+    if (cudaEventQuery(h->ev[2 * i]) == cudaSuccess) {
+      if (n_out < max_out) { kinds[n_out] = h->ev_kind[i]; slots[n_out] = i; ++n_out; }
+    } else {
+      ++waiting;
+    }
   }
   (void)cudaGetLastError();
-  return -1;
+  if (not_started) *not_started = waiting;
+  return n_out;
 }
 
 int dinoseg_profile_num_kinds(void) { return K_COUNT; }

@@ -167,10 +167,11 @@ int dinoseg_last_launch_count(const dinoseg_t* h);
 int dinoseg_profile_enable(dinoseg_t* h, int on);
 /* restrict the events to the kinds whose bit is set (default: all kinds) */
 int dinoseg_profile_set_mask(dinoseg_t* h, uint32_t kind_mask);
-/* Diagnostic for a forward that does not finish; may be called from another host thread: the kind (see
- * dinoseg_profile_kind_name) of the first profiled launch that has started and not ended; -1: none; -2: profiling is
- * off; -3: a launch is pending that has not even started (something before it is stuck).  slot (optional): its index. */
-int dinoseg_debug_pending_kind(dinoseg_t* h, int* slot);
+/* Diagnostic for work that does not finish; may be called from another host thread while the launching thread is
+ * blocked: the profiled launches (dinoseg_profile_enable) that have started and not ended, i.e. the kernels running or
+ * stuck right now (kinds[] as in dinoseg_profile_kind_name, slots[] = launch index since profiling was enabled).
+ * Returns the number written (<= max_out), -2 if profiling is off; *not_started = launches still queued behind them. */
+int dinoseg_debug_pending_kinds(dinoseg_t* h, int* kinds, int* slots, int max_out, int* not_started);
 int dinoseg_profile_num_kinds(void);
 const char* dinoseg_profile_kind_name(int kind);
 int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds);
