@@ -391,8 +391,11 @@ def main():
         running = [f"{lib.dinoseg_profile_kind_name(kinds[i]).decode()}#{slots[i]}" for i in range(max(n, 0))]
         smi = subprocess.run(["nvidia-smi", "--query-gpu=utilization.gpu,clocks.sm,power.draw,memory.used",
                               "--format=csv,noheader", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout.strip()
+        hb = (C.c_int * 160)()
+        nhb = lib.dinoseg_debug_heartbeat(hb, 160)
+        live = {i: hb[i] for i in range(max(nhb, 0)) if hb[i] > 0}      # SM -> kernel code * 10 + stage (hb_mark)
         return (f"launches started and not finished: {running if n >= 0 else 'profiling off'}; queued behind them: "
-                f"{waiting.value}; nvidia-smi: {smi}")
+                f"{waiting.value}; nvidia-smi: {smi}; tcgen05 CTAs still resident (sm: code*10+stage): {live}")
 
     STALL_HOOKS.append(gpu_state)
     PHASE[0] = "warm-up"

@@ -53,6 +53,7 @@ SIGNATURES = {
     "dinoseg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_profile_set_mask": (C.c_int, [C.c_void_p, C.c_uint32]),
     "dinoseg_debug_pending_kinds": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "dinoseg_debug_heartbeat": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "dinoseg_profile_num_kinds": (C.c_int, []),
     "dinoseg_profile_kind_name": (C.c_char_p, [C.c_int]),
     "dinoseg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),

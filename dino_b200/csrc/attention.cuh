@@ -53,6 +53,7 @@ struct AttnParams {
   int lone;             // 1: the number of query tiles is odd (one tail tile per (frame, head), see att_decode)
   int num_items;        // regular + tail items
   long long* timing;    // debug (DSG_ATTN_TIMING builds): [grid][2 warpgroups][8] phase cycle totals
+  int* hb;              // diagnostic heartbeat (see hb_mark), may be null
 };
 
 #ifdef DSG_ATTN_TIMING
@@ -493,6 +494,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int lane = threadIdx.x & 31;
   const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
 
+  constexpr int HB_CODE = 300 + SMW;
+  hb_mark(p.hb, HB_CODE, 1);
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
@@ -514,6 +517,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  hb_mark(p.hb, HB_CODE, 2);
 
   if (warp < 4) {
     // Registers move from the producer warpgroup to the softmax warps.  The budget is the CTA's register pool AT LAUNCH
@@ -642,9 +646,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     }
   }
 
+  hb_mark(p.hb, HB_CODE, 3);
   tc_fence_before();
   __syncthreads();
+  hb_mark(p.hb, HB_CODE, 4);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  hb_mark(p.hb, HB_CODE, 0);
 }
 
 }  // namespace dsg

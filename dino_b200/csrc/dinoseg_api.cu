@@ -129,6 +129,7 @@ bool make_tmap_qkv(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint
 // -----------------------------------------------------------------------------------------
 constexpr int kAttnStages = 6;   // 6 x 32 KB K|V stages + 2 Q tiles = 224 KB (dual tail items run two 3-deep streams)
 long long* g_attn_timing = nullptr;   // debug: device buffer for the DSG_*_TIMING builds
+int* g_heartbeat = nullptr;           // diagnostic: per-SM (kernel, stage) marks of the tcgen05 kernels (hb_mark), 1024 ints
 
 // The weight tensor maps come in two flavours: full 128-row granules (plain kernel) and 64-row half granules (cluster
 // kernel: each CTA of a cta_group::2 pair holds one half of the B operand).
@@ -145,6 +146,7 @@ cudaError_t launch_mlp_fused(const CUtensorMap& a, const CUtensorMap& w1, const 
   }
   MlpParams pp = p;
   pp.timing = g_attn_timing;
+  pp.hb = g_heartbeat;
   const int m_blocks = (p.M + MLP_BM - 1) / MLP_BM;
   if (!pair) {
     const int grid = m_blocks < num_sms ? m_blocks : num_sms;
@@ -192,6 +194,7 @@ cudaError_t launch_gemm_tt(const CUtensorMap& a, const CUtensorMap& w, const CUt
   const int grid = units < num_sms ? int(units) : num_sms;    // persistent: one CTA per SM
   GemmParams pp = p;
   pp.timing = g_attn_timing;
+  pp.hb = g_heartbeat;
   kern<<<grid, GEMM_THREADS, smem, s>>>(a, w, out, add, pp);
   return cudaGetLastError();
 }
@@ -219,6 +222,7 @@ cudaError_t launch_gemm_pair_t(const CUtensorMap& a, const CUtensorMap& w, const
   const int max_pairs = num_sms / 2;
   GemmParams pp = p;
   pp.timing = g_attn_timing;
+  pp.hb = g_heartbeat;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * unsigned(units < max_pairs ? units : max_pairs));
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -311,6 +315,7 @@ cudaError_t launch_attention_t(const CUtensorMap& qkv, const AttnParams& p, int 
 
 cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
   p.timing = g_attn_timing;
+  p.hb = g_heartbeat;
   attn_plan_items(p);
   return attn_smw() == 8 ? launch_attention_t<8>(qkv, p, num_sms, s) : launch_attention_t<4>(qkv, p, num_sms, s);
 }
@@ -708,6 +713,10 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   if (!get_encode()) DSG_FAIL(null_h, "cuTensorMapEncodeTiled not available from the driver");
   DSG_CUDA(null_h, cudaSetDevice(device));
 
+  if (!g_heartbeat) {                     // one array per process, never freed (diagnostics)
+    if (cudaMalloc(&g_heartbeat, 1024 * sizeof(int)) == cudaSuccess) cudaMemset(g_heartbeat, 0, 1024 * sizeof(int));
+    else { g_heartbeat = nullptr; (void)cudaGetLastError(); }
+  }
   dinoseg* h = new dinoseg();
   h->cfg = *cfg;
   h->device = device;
@@ -944,6 +953,18 @@ int dinoseg_debug_pending_kinds(dinoseg_t* h, int* kinds, int* slots, int max_ou
   (void)cudaGetLastError();
   if (not_started) *not_started = waiting;
   return n_out;
+}
+
+// Copies the heartbeat array (hb_mark: entry [sm] = kernel code * 10 + stage while a tcgen05 kernel's CTA sits on that
+// SM, negative after it left) to the host on a stream of its own, so that it works while other streams are stuck.
+// kernel codes: 100 + EPI*10 + 2*RES_A + PAIR = GEMM, 200 + PAIR = fused MLP, 300 + SMW = attention.
+int dinoseg_debug_heartbeat(int* host_out, int n) {
+  if (!host_out || n < 1 || !g_heartbeat) return -1;
+  static cudaStream_t diag = nullptr;
+  if (!diag && cudaStreamCreateWithFlags(&diag, cudaStreamNonBlocking) != cudaSuccess) return -2;
+  if (n > 1024) n = 1024;
+  if (cudaMemcpyAsync(host_out, g_heartbeat, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, diag) != cudaSuccess) return -3;
+  return cudaStreamSynchronize(diag) == cudaSuccess ? n : -4;
 }
 
 int dinoseg_profile_num_kinds(void) { return K_COUNT; }

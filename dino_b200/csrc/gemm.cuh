@@ -51,6 +51,7 @@ struct GemmParams {
   int reverse;          // 1: row blocks are processed last to first (L2 reuse between consecutive kernels)
   int a_wrap;           // > 0: A has only a_wrap columns and the k index wraps (bf16x3 operand stored as [hi | lo])
   long long* timing;    // debug (DSG_GEMM_TIMING builds): [grid][3 roles][8] cycle totals
+  int* hb;              // diagnostic heartbeat (see hb_mark), may be null
 };
 
 #ifdef DSG_GEMM_TIMING
@@ -199,6 +200,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mt = PAIR ? unit * 2 + int(cta_rank) : unit;
   };
 
+  constexpr int HB_CODE = 100 + EPI * 10 + (RES_A ? 2 : 0) + (PAIR ? 1 : 0);
+  hb_mark(p.hb, HB_CODE, 1);
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -231,6 +234,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  hb_mark(p.hb, HB_CODE, 2);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -505,13 +509,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (leader) tma_store_wait<0>();               // all output bytes are globally visible before exit
   }
 
+  hb_mark(p.hb, HB_CODE, 3);
   tc_fence_before();
   __syncthreads();
+  hb_mark(p.hb, HB_CODE, 4);
   if constexpr (PAIR) cluster_sync_all();          // both CTAs are done with each other's barriers and TMEM
+  hb_mark(p.hb, HB_CODE, 5);
   if (warp == 1) {
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  hb_mark(p.hb, HB_CODE, 0);
 }
 
 }  // namespace dsg

@@ -42,6 +42,7 @@ struct MlpParams {
   const float* ln_b;          // [384]
   float ln_eps;
   long long* timing;          // debug (DSG_MLP_TIMING): [grid][2 roles][8] cycle totals
+  int* hb;                    // diagnostic heartbeat (see hb_mark), may be null
 };
 
 #ifdef DSG_MLP_TIMING
@@ -157,6 +158,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else mbar_arrive(bar);
   };
 
+  constexpr int HB_CODE = 200 + (PAIR ? 1 : 0);
+  hb_mark(p.hb, HB_CODE, 1);
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW1);
@@ -182,6 +185,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  hb_mark(p.hb, HB_CODE, 2);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -576,13 +580,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (leader) tma_store_wait<0>();
   }
 
+  hb_mark(p.hb, HB_CODE, 3);
   tc_fence_before();
   __syncthreads();
+  hb_mark(p.hb, HB_CODE, 4);
   if constexpr (PAIR) cluster_sync_all();           // both CTAs are done with each other's barriers and TMEM
+  hb_mark(p.hb, HB_CODE, 5);
   if (warp == 1) {
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  hb_mark(p.hb, HB_CODE, 0);
 }
 
 }  // namespace dsg

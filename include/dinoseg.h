@@ -172,6 +172,10 @@ int dinoseg_profile_set_mask(dinoseg_t* h, uint32_t kind_mask);
  * stuck right now (kinds[] as in dinoseg_profile_kind_name, slots[] = launch index since profiling was enabled).
  * Returns the number written (<= max_out), -2 if profiling is off; *not_started = launches still queued behind them. */
 int dinoseg_debug_pending_kinds(dinoseg_t* h, int* kinds, int* slots, int max_out, int* not_started);
+/* Diagnostic: per-SM marks of the tcgen05 kernels (entry [sm] = kernel code * 10 + stage while a CTA of that kernel
+ * sits on the SM, negative once it has left; codes and stages: csrc/ptx.cuh hb_mark, csrc/dinoseg_api.cu).  Copied on a
+ * stream of its own: usable from another thread while the data streams are stuck.  Returns n or < 0. */
+int dinoseg_debug_heartbeat(int* host_out, int n);
 int dinoseg_profile_num_kinds(void);
 const char* dinoseg_profile_kind_name(int kind);
 int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds);
