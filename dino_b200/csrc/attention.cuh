@@ -650,8 +650,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   tc_fence_before();
   __syncthreads();
   hb_mark(p.hb, HB_CODE, 4);
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-  hb_mark(p.hb, HB_CODE, 0);
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, TMEM_COLS);
+    hb_mark_left(p.hb, HB_CODE);                     // by the deallocating warp: a CTA stuck in dealloc stays visible
+  }
 }
 
 }  // namespace dsg

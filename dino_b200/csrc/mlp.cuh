@@ -589,8 +589,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
+    hb_mark_left(p.hb, HB_CODE);                     // by the deallocating warp: a CTA stuck in dealloc stays visible
   }
-  hb_mark(p.hb, HB_CODE, 0);
 }
 
 }  // namespace dsg

@@ -512,14 +512,22 @@ __device__ __forceinline__ float2 exp2_poly_x2(float2 x) {
   return r;
 }
 // Diagnostic heartbeat: thread 0 of a CTA records (kernel code, stage) in a per-SM slot of a device array, a negative
-// value when the CTA leaves.  Read by dinoseg_debug_heartbeat when something does not finish: which kernel sits on
+// value once the CTA has deallocated its TMEM.  Read by dinoseg_debug_heartbeat when something does not finish: which kernel sits on
 // which SM, and how far it got (1 entered, 2 past TMEM allocation + first barrier, 3 work done, 4 past the last CTA
 // barrier, 5 past the cluster barrier).  One store per stage per CTA: no measurable cost.
 __device__ __forceinline__ void hb_mark(int* hb, int code, int stage) {
   if (hb != nullptr && threadIdx.x == 0) {
     uint32_t sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-    reinterpret_cast<volatile int*>(hb)[sm & 1023u] = stage > 0 ? code * 10 + stage : -(code * 10);
+    reinterpret_cast<volatile int*>(hb)[sm & 1023u] = code * 10 + stage;
+  }
+}
+// called by the warp that has just deallocated TMEM (its first lane writes)
+__device__ __forceinline__ void hb_mark_left(int* hb, int code) {
+  if (hb != nullptr && (threadIdx.x & 31) == 0) {
+    uint32_t sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    reinterpret_cast<volatile int*>(hb)[sm & 1023u] = -(code * 10);
   }
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
