@@ -486,9 +486,11 @@ void expand_labels_host(const uint8_t* low, int64_t* out, int g, int p) {
   if (nt) _mm_sfence();
 }
 
+// One slot of the host-path pipeline: device staging for a chunk of frames, a workspace and staging for its results.
+// in_done: the chunk's frames have arrived; comp_done: its kernels have finished (the frames / workspace may be
+// reused); out_done: its results have left (lowres / labels staging may be reused).
 struct HostLane {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
   float* frames = nullptr; size_t frames_cap = 0;
   void* ws = nullptr; size_t ws_cap = 0;
   uint8_t* lowres = nullptr; size_t lowres_cap = 0;
@@ -547,8 +549,14 @@ struct dinoseg {
   int ev_used = 0;
 
   // predict_host pipeline (lazily created)
+  // Three slots, THREE STREAMS with fixed roles: copy-in (H2D), compute (every kernel), copy-out (D2H).  All kernels
+  // of the host path run on the ONE compute stream, in order: copies overlap kernels, kernels never overlap kernels.
+  // (Round 1 gave every slot its own stream, so kernels of different chunks ran concurrently; a cluster of a
+  // cta_group::2 kernel that starts while another stream's kernels are resident can block in tcgen05.alloc for ever -
+  // DESIGN.md section 4.5 - and the overlap bought nothing: each kernel is persistent and fills the GPU by itself.)
   static constexpr int kLanes = 3;
   HostLane lanes[kLanes];
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   cudaEvent_t host_start = nullptr;
   int host_chunk = 0;               // frames per pipeline chunk; 0 = automatic (see pick_host_chunk)
   // host label maps: 1 = copy the low-res maps (g*g bytes per frame) to the host and expand them to int64 there with
@@ -561,8 +569,7 @@ struct dinoseg {
   static constexpr int kTickets = 4;
   struct Ticket {
     int64_t id = 0;
-    int nlanes = 0;
-    cudaEvent_t lane_done[kLanes] = {};
+    cudaEvent_t done = nullptr;       // recorded on the copy-out stream after the submission's last copy
     bool expand = false;
     std::vector<int> plan;            // frames per chunk
     std::vector<cudaEvent_t> chunk_done;
@@ -729,6 +736,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0 ? 1 : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_FUSE_LN")) h->fuse_ln = atoi(mode) != 0;         // measurement override
+  if (const char* mode = getenv("DINOSEG_HOST_CHUNK")) h->host_chunk = atoi(mode) > 0 ? atoi(mode) : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
     const int m = atoi(mode);
@@ -818,21 +826,24 @@ void dinoseg_destroy(dinoseg_t* h) {
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   if (h->pos) cudaFree(h->pos);
+  for (cudaStream_t st : {h->s_in, h->s_comp, h->s_out})
+    if (st) cudaStreamSynchronize(st);
   for (HostLane& l : h->lanes) {
-    if (l.stream) cudaStreamSynchronize(l.stream);
     if (l.frames) cudaFree(l.frames);
     if (l.ws) cudaFree(l.ws);
     if (l.lowres) cudaFree(l.lowres);
     if (l.labels) cudaFree(l.labels);
-    if (l.done) cudaEventDestroy(l.done);
-    if (l.stream) cudaStreamDestroy(l.stream);
+    for (cudaEvent_t e : {l.in_done, l.comp_done, l.out_done})
+      if (e) cudaEventDestroy(e);
   }
+  for (cudaStream_t st : {h->s_in, h->s_comp, h->s_out})
+    if (st) cudaStreamDestroy(st);
   if (h->host_start) cudaEventDestroy(h->host_start);
   delete h->pool;
   for (dinoseg::Ticket& t : h->tickets) {
     if (t.low_stage) cudaFreeHost(t.low_stage);
     for (cudaEvent_t e : t.chunk_done) cudaEventDestroy(e);
-    for (cudaEvent_t e : t.lane_done) if (e) cudaEventDestroy(e);
+    if (t.done) cudaEventDestroy(t.done);
   }
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
@@ -1250,8 +1261,7 @@ static int ticket_wait(dinoseg_t* h, dinoseg::Ticket& t) {
     }
     h->pool->wait_all();
   }
-  for (int k = 0; k < t.nlanes; ++k)
-    if (cudaEventSynchronize(t.lane_done[k]) != cudaSuccess) rc = -1;
+  if (cudaEventSynchronize(t.done) != cudaSuccess) rc = -1;
   t.id = 0;
   if (rc != 0) { h->err = "dinoseg_predict_host_wait: a CUDA operation of the submission failed"; }
   return rc;
@@ -1269,20 +1279,27 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
   if (!tk) DSG_FAIL(h, "%s: %d submissions are outstanding; call dinoseg_predict_host_wait first", who, dinoseg::kTickets);
   DSG_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // The batch is cut into chunks that go round-robin through three lanes (stream + staging + workspace
-  // each): H2D copy, forward and D2H copy of a chunk are ordered on its lane's stream, and the copies
-  // of one lane overlap the kernels of the other.  Frames are independent, so chunking does not change
-  // any result bit.  Consecutive submissions queue behind each other on the same lanes: the first H2D copy of
-  // submission k+1 overlaps the last kernels and the last D2H copy of submission k.
+  // The batch is cut into chunks that go round-robin through three slots (frame staging + workspace + result staging):
+  // the H2D copy of chunk c+1 (copy-in stream) and the D2H copy of chunk c-1 (copy-out stream) overlap the kernels of
+  // chunk c (compute stream).  Frames are independent, so chunking does not change any result bit.  Consecutive
+  // submissions queue behind each other on the same three streams: the first H2D copy of submission k+1 overlaps the
+  // last kernels and the last D2H copy of submission k.
   const int chunk = pick_host_chunk(h, batch);
   const size_t frame_bytes = pp ? size_t(pp->src_h) * pp->src_w * 3 : size_t(3) * h->res * h->res * sizeof(float);
   const size_t W = size_t(h->g) * h->p_rep;
   const size_t label_elems = W * W;
   const size_t wbytes = dinoseg_workspace_bytes(h, chunk);
   if (!h->host_start) DSG_CUDA(h, cudaEventCreateWithFlags(&h->host_start, cudaEventDisableTiming));
-  auto grow = [&](HostLane& l, void** p, size_t* cap, size_t need) -> cudaError_t {
+  if (!h->s_in) DSG_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  if (!h->s_comp) DSG_CUDA(h, cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+  if (!h->s_out) DSG_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  if (!tk->done) DSG_CUDA(h, cudaEventCreateWithFlags(&tk->done, cudaEventDisableTiming));
+  auto grow = [&](HostLane&, void** p, size_t* cap, size_t need) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
-    if (*p) { cudaStreamSynchronize(l.stream); cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (*p) {                                  // a buffer of an earlier, smaller submission: nothing may still use it
+      cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_comp); cudaStreamSynchronize(h->s_out);
+      cudaFree(*p); *p = nullptr; *cap = 0;
+    }
     cudaError_t e = cudaMalloc(p, need);
     if (e == cudaSuccess) *cap = need;
     return e;
@@ -1336,9 +1353,8 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
   }
   for (int k = 0; k < nlanes; ++k) {
     HostLane& l = h->lanes[k];
-    if (!l.stream) DSG_CUDA(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-    if (!l.done) DSG_CUDA(h, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-    if (!tk->lane_done[k]) DSG_CUDA(h, cudaEventCreateWithFlags(&tk->lane_done[k], cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&l.in_done, &l.comp_done, &l.out_done})
+      if (!*e) DSG_CUDA(h, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     const size_t ws_before = l.ws_cap;
     DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.frames), &l.frames_cap, size_t(chunk) * frame_bytes));
     DSG_CUDA(h, grow(l, &l.ws, &l.ws_cap, wbytes));
@@ -1349,48 +1365,58 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
   }
   // From here on work is in flight: every error exit drains the lanes first, so that the caller may free its buffers.
   auto enqueue = [&]() -> int {
-    // lanes start after whatever the caller queued on its stream
+    // the pipeline starts after whatever the caller queued on its stream
     DSG_CUDA(h, cudaEventRecord(h->host_start, s));
-    for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaStreamWaitEvent(h->lanes[k].stream, h->host_start, 0));
+    DSG_CUDA(h, cudaStreamWaitEvent(h->s_in, h->host_start, 0));
     int f0 = 0;
     for (int c = 0; c < nchunks; f0 += plan[c], ++c) {
       HostLane& l = h->lanes[c % nlanes];
       const int nb = plan[c];
       if (nb <= 0) continue;
+      // copy-in: the slot's frame staging is free once the kernels of its previous chunk have finished
+      // (waiting on an event that has never been recorded is a no-op: first use of the slot)
+      DSG_CUDA(h, cudaStreamWaitEvent(h->s_in, l.comp_done, 0));
       DSG_CUDA(h, cudaMemcpyAsync(l.frames, static_cast<const uint8_t*>(host_frames) + size_t(f0) * frame_bytes,
-                                  size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, l.stream));
+                                  size_t(nb) * frame_bytes, cudaMemcpyHostToDevice, h->s_in));
+      DSG_CUDA(h, cudaEventRecord(l.in_done, h->s_in));
+      // compute: after the frames have arrived and the slot's previous results have left
+      DSG_CUDA(h, cudaStreamWaitEvent(h->s_comp, l.in_done, 0));
+      DSG_CUDA(h, cudaStreamWaitEvent(h->s_comp, l.out_done, 0));
       if (bind_workspace(h, l.bufs, l.ws, l.ws_cap, nb) != 0) return -1;
       if (forward_impl(h, l.bufs, pp ? nullptr : l.frames, pp ? reinterpret_cast<const uint8_t*>(l.frames) : nullptr, pp, nb,
-                       nullptr, l.lowres, (want_labels && !expand) ? l.labels : nullptr, l.stream) != 0)
+                       nullptr, l.lowres, (want_labels && !expand) ? l.labels : nullptr, h->s_comp) != 0)
         return -1;
+      DSG_CUDA(h, cudaEventRecord(l.comp_done, h->s_comp));
+      // copy-out
+      DSG_CUDA(h, cudaStreamWaitEvent(h->s_out, l.comp_done, 0));
       if (expand) {
         DSG_CUDA(h, cudaMemcpyAsync(tk->low_stage + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
-                                    l.stream));
-        DSG_CUDA(h, cudaEventRecord(tk->chunk_done[c], l.stream));
-        continue;
+                                    h->s_out));
+        DSG_CUDA(h, cudaEventRecord(tk->chunk_done[c], h->s_out));
+      } else {
+        if (host_lowres)
+          DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
+                                      h->s_out));
+        if (want_labels)
+          DSG_CUDA(h, cudaMemcpyAsync(host_labels + size_t(f0) * label_elems, l.labels,
+                                      size_t(nb) * label_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, h->s_out));
       }
-      if (host_lowres)
-        DSG_CUDA(h, cudaMemcpyAsync(host_lowres + size_t(f0) * h->P, l.lowres, size_t(nb) * h->P, cudaMemcpyDeviceToHost,
-                                    l.stream));
-      if (want_labels)
-        DSG_CUDA(h, cudaMemcpyAsync(host_labels + size_t(f0) * label_elems, l.labels,
-                                    size_t(nb) * label_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, l.stream));
+      DSG_CUDA(h, cudaEventRecord(l.out_done, h->s_out));
     }
-    // (the caller's stream is NOT made to wait for the lanes: the results are host buffers, complete when
+    // (the caller's stream is NOT made to wait for the pipeline: the results are host buffers, complete when
     // dinoseg_predict_host_wait returns, and a wait here would serialise consecutive submissions)
-    for (int k = 0; k < nlanes; ++k) DSG_CUDA(h, cudaEventRecord(tk->lane_done[k], h->lanes[k].stream));
+    DSG_CUDA(h, cudaEventRecord(tk->done, h->s_out));      // the copy-out stream is in order: one event covers all chunks
     return 0;
   };
   if (enqueue() != 0) {
     const std::string why = h->err;
-    for (int k = 0; k < nlanes; ++k)
-      if (h->lanes[k].stream) cudaStreamSynchronize(h->lanes[k].stream);
+    for (cudaStream_t st : {h->s_in, h->s_comp, h->s_out})
+      if (st) cudaStreamSynchronize(st);
     if (h->pool) h->pool->wait_all();
     (void)cudaGetLastError();
     h->err = why;
     return -1;
   }
-  tk->nlanes = nlanes;
   tk->expand = expand;
   tk->host_lowres = host_lowres;
   tk->host_labels = host_labels;
