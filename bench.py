@@ -394,6 +394,10 @@ def main():
         hb = (C.c_int * 160)()
         nhb = lib.dinoseg_debug_heartbeat(hb, 160)
         live = {i: hb[i] for i in range(max(nhb, 0)) if hb[i] > 0}      # SM -> kernel code * 10 + stage (hb_mark)
+        if os.environ.get("DINOSEG_BENCH_HB_WIDE") == "1":                # experimental builds: second half of the array
+            hb2 = (C.c_int * 1024)()
+            if lib.dinoseg_debug_heartbeat(hb2, 1024) > 0:
+                live = {"stage": live, "alloc_returned": {i: hb2[512 + i] for i in live}}
         return (f"launches started and not finished: {running if n >= 0 else 'profiling off'}; queued behind them: "
                 f"{waiting.value}; nvidia-smi: {smi}; tcgen05 CTAs still resident (sm: code*10+stage): {live}")
 
