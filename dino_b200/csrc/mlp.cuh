@@ -176,6 +176,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(acc2_empty, 4 * NCTA);
     fence_mbar_init();
   }
+  // CTA pairs: BOTH CTAs must be running before either issues tcgen05.alloc.cta_group::2.  The two CTAs of a cluster
+  // do not necessarily start at the same time: when kernels of other streams occupy the GPU, one SM of the pair can
+  // drain much later than the other.  An allocation issued while the peer CTA is not resident yet returns, but the
+  // peer's own allocation then blocks for ever (observed: rank 0 past the allocation, rank 1 stuck inside it; never
+  // with one stream, where the two CTAs start together).  Hence a cluster barrier first - as CUTLASS' 2-SM kernels do
+  // (cluster-wide pipeline-init barrier before the TMEM allocation) - which also publishes the barrier initialisation.
+  if constexpr (PAIR) cluster_sync_all();
   if (warp == 1) {
     if constexpr (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
     else tmem_alloc(tmem_slot, TMEM_COLS);
