@@ -469,14 +469,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // r*128 + (((c%64)/8 ^ (r&7)) << 4) + (c%8)*2.  Rows >= M are written as zeros (what TMA's fill does).
     const bool fuse_ln = p.ln_g != nullptr;
     const int ow = warp - 10;                       // 0..3
-    float4 gm[3], bt[3];
-    if (fuse_ln) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        gm[i] = __ldg(reinterpret_cast<const float4*>(p.ln_g) + i * 32 + lane);
-        bt[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i * 32 + lane);
-      }
-    }
     auto prefetch_block = [&](int bi) {             // the block's 128 rows of x -> L2 (192 KB: 12 lines per thread)
       const int r0 = block_row0(bi);
       const char* base = reinterpret_cast<const char*>(p.x + size_t(r0) * MLP_D);
@@ -484,50 +476,66 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (size_t off = size_t(threadIdx.x - 320) * 128; off < bytes; off += 128 * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
     };
+    // rows r0 + ow*32 + rb .. +3 of x into registers (three float4 per lane and row)
+    auto ln_load = [&](float4 (&v)[4][3], int r0, int rb) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = r0 + ow * 32 + rb + q;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(row) * MLP_D);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[q][i] = row < p.M ? __ldg(xr + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    // normalise four rows and write them into sA (gamma / beta come from L1: keeping them in registers would cost 24)
+    auto ln_store = [&](const float4 (&v)[4][3], int r0, int rb) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = ow * 32 + rb + q;             // row inside the block
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sum += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / MLP_D);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
+          sq += (a * a + b * b) + (c * c + d * d);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * (1.0f / MLP_D) + p.ln_eps);
+        const bool live = r0 + r < p.M;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g) + i * 32 + lane);
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i * 32 + lane);
+          const float a = (v[q][i].x - mean) * rstd * gm.x + bt.x, b = (v[q][i].y - mean) * rstd * gm.y + bt.y;
+          const float c = (v[q][i].z - mean) * rstd * gm.z + bt.z, d = (v[q][i].w - mean) * rstd * gm.w + bt.w;
+          uint2 o;
+          o.x = live ? pack_bf16x2(a, b) : 0u;
+          o.y = live ? pack_bf16x2(c, d) : 0u;
+          // columns i*128 + lane*4 .. +3: k-block 2i + lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
+          uint8_t* dst = sA + size_t(2 * i + (lane >> 4)) * MLP_GRAN + r * 128 + ((((lane & 15) >> 1) ^ (r & 7)) << 4) +
+                         (lane & 1) * 8;
+          *reinterpret_cast<uint2*>(dst) = o;
+        }
+      }
+    };
+    // The fill is latency-bound (a row is 1.5 KB spread over L2 slices), so the loads run one batch of four rows ahead
+    // of the arithmetic, and the first batch is requested before the wait for the A buffer.
     auto ln_fill = [&](int bi) {
       const int r0 = block_row0(bi);
+      float4 va[4][3], vb[4][3];
+      ln_load(va, r0, 0);
       if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1); // the last MMA1 of the previous block has read A
-      for (int rb = 0; rb < 32; rb += 4) {
-        float4 v[4][3];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int row = r0 + ow * 32 + rb + q;
-          const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(row) * MLP_D);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) v[q][i] = row < p.M ? __ldg(xr + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = ow * 32 + rb + q;           // row inside the block
-          float sum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) sum += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          const float mean = sum * (1.0f / MLP_D);
-          float sq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
-            sq += (a * a + b * b) + (c * c + d * d);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-          const float rstd = rsqrtf(sq * (1.0f / MLP_D) + p.ln_eps);
-          const bool live = r0 + r < p.M;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float a = (v[q][i].x - mean) * rstd * gm[i].x + bt[i].x, b = (v[q][i].y - mean) * rstd * gm[i].y + bt[i].y;
-            const float c = (v[q][i].z - mean) * rstd * gm[i].z + bt[i].z, d = (v[q][i].w - mean) * rstd * gm[i].w + bt[i].w;
-            uint2 o;
-            o.x = live ? pack_bf16x2(a, b) : 0u;
-            o.y = live ? pack_bf16x2(c, d) : 0u;
-            // columns i*128 + lane*4 .. +3: k-block 2i + lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
-            uint8_t* dst = sA + size_t(2 * i + (lane >> 4)) * MLP_GRAN + r * 128 + ((((lane & 15) >> 1) ^ (r & 7)) << 4) +
-                           (lane & 1) * 8;
-            *reinterpret_cast<uint2*>(dst) = o;
-          }
-        }
+#pragma unroll 1
+      for (int rb = 0; rb < 32; rb += 8) {
+        ln_load(vb, r0, rb + 4);
+        ln_store(va, r0, rb);
+        if (rb + 8 < 32) ln_load(va, r0, rb + 8);
+        ln_store(vb, r0, rb + 4);
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the UMMA reads of sA
       __syncwarp();
