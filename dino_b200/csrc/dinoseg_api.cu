@@ -557,6 +557,7 @@ struct dinoseg {
   static constexpr int kLanes = 3;
   HostLane lanes[kLanes];
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  unsigned slot_seq = 0;            // chunks enqueued so far (slot of a chunk = slot_seq % kLanes)
   cudaEvent_t host_start = nullptr;
   int host_chunk = 0;               // frames per pipeline chunk; 0 = automatic (see pick_host_chunk)
   // host label maps: 1 = copy the low-res maps (g*g bytes per frame) to the host and expand them to int64 there with
@@ -1197,11 +1198,25 @@ int dinoseg_forward(dinoseg_t* h, const float* frames, int batch, float* logprob
                       static_cast<cudaStream_t>(stream));
 }
 
-// Frames per pipeline chunk: small enough to overlap the copies with the kernels (6..16 frames), and such that
-// the 128-token row blocks of a chunk fill whole waves of the persistent kernels (one CTA per SM).
-// Swept on B200 at 480 px, batch 64: 5 -> 5474, 8 -> 6067, 10 -> 6163, 16 -> 5796, 21 -> 5885, 32 -> 5367 frames/s.
-static int pick_host_chunk(const dinoseg* h, int batch) {
+// Frames per pipeline chunk.
+// streaming == false (the synchronous call, nothing else in flight): small enough to overlap the copies with the
+// kernels inside ONE call (6..16 frames), and such that the 128-token row blocks of a chunk fill whole waves of the
+// persistent kernels (one CTA per SM).  Swept on B200 at 480 px, batch 64: 5 -> 5474, 8 -> 6067, 10 -> 6163,
+// 16 -> 5796, 21 -> 5885, 32 -> 5367 frames/s.
+// streaming == true (dinoseg_predict_host_submit: the caller keeps several submissions in flight): the copies of one
+// submission overlap the kernels of its neighbours, so chunks are as large as a 2 GB workspace allows (64 frames at
+// 480 px, 16 at 960 px) - every kernel then runs at the efficiency of the device path instead of paying its tail
+// wave once per ~10 frames.
+static int pick_host_chunk(const dinoseg* h, int batch, bool streaming) {
   if (h->host_chunk > 0) return h->host_chunk < batch ? h->host_chunk : batch;
+  if (streaming) {
+    const long long max_rows = 262144;                       // ~2 GB of workspace for ViT-S
+    long long c = max_rows / h->Ntok;
+    if (c < 1) c = 1;
+    if (c >= batch) return batch;
+    const int parts = int((batch + c - 1) / c);              // equal parts rather than full chunks plus a remainder
+    return (batch + parts - 1) / parts;
+  }
   int best = batch < 6 ? batch : 6;
   double best_eff = -1.0;
   for (int c = 6; c <= 16 && c <= batch; ++c) {
@@ -1271,7 +1286,8 @@ static int ticket_wait(dinoseg_t* h, dinoseg::Ticket& t) {
 // uint8 HWC frames of src_h x src_w pixels (pp != nullptr).  Enqueues the whole submission and returns its ticket
 // (> 0) without waiting for the GPU; < 0 on error (nothing is left in flight then).
 static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, const PreprocParams* pp, int batch,
-                                        uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who) {
+                                        uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who,
+                                        bool streaming) {
   if (!h) return -1;
   if (h->res == 0) DSG_FAIL(h, "%s: call dinoseg_set_resolution first", who);
   if (!host_frames || batch <= 0) DSG_FAIL(h, "%s: bad arguments", who);
@@ -1284,7 +1300,7 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
   // chunk c (compute stream).  Frames are independent, so chunking does not change any result bit.  Consecutive
   // submissions queue behind each other on the same three streams: the first H2D copy of submission k+1 overlaps the
   // last kernels and the last D2H copy of submission k.
-  const int chunk = pick_host_chunk(h, batch);
+  const int chunk = pick_host_chunk(h, batch, streaming);
   const size_t frame_bytes = pp ? size_t(pp->src_h) * pp->src_w * 3 : size_t(3) * h->res * h->res * sizeof(float);
   const size_t W = size_t(h->g) * h->p_rep;
   const size_t label_elems = W * W;
@@ -1310,6 +1326,8 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
   plan.clear();
   if (batch <= chunk) {
     plan.push_back(batch);
+  } else if (streaming) {
+    for (int rest = batch; rest > 0; rest -= chunk) plan.push_back(rest < chunk ? rest : chunk);
   } else {
     int rest = batch;
     const int rem = batch % chunk;
@@ -1320,7 +1338,9 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
     plan.push_back(rest);           // = chunk, or the other half of a split chunk when chunk divides batch
   }
   const int nchunks = int(plan.size());
-  const int nlanes = nchunks < dinoseg::kLanes ? nchunks : dinoseg::kLanes;
+  // slots are taken round-robin ACROSS submissions (h->slot_seq), so that a one-chunk submission does not wait for the
+  // buffers of the one before it
+  const int nlanes = dinoseg::kLanes;
   const bool want_labels = host_labels && label_elems;
   // Label maps: the int64 [g*p, g*p] map is 512x the size of the low-res map it replicates.  With host expansion the
   // GPU ships the low-res maps (3.6 KB per frame at 480 px) and worker threads expand them into the caller's buffer
@@ -1351,8 +1371,8 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
       tk->chunk_done.push_back(e);
     }
   }
-  for (int k = 0; k < nlanes; ++k) {
-    HostLane& l = h->lanes[k];
+  // a slot's events and buffers are created / grown when a chunk first needs them
+  auto prepare_slot = [&](HostLane& l) -> int {
     for (cudaEvent_t* e : {&l.in_done, &l.comp_done, &l.out_done})
       if (!*e) DSG_CUDA(h, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     const size_t ws_before = l.ws_cap;
@@ -1362,7 +1382,8 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
     if (want_labels && !expand)
       DSG_CUDA(h, grow(l, reinterpret_cast<void**>(&l.labels), &l.labels_cap, size_t(chunk) * label_elems * sizeof(int64_t)));
     if (l.ws_cap != ws_before) l.bufs.base = nullptr;
-  }
+    return 0;
+  };
   // From here on work is in flight: every error exit drains the lanes first, so that the caller may free its buffers.
   auto enqueue = [&]() -> int {
     // the pipeline starts after whatever the caller queued on its stream
@@ -1370,9 +1391,10 @@ static int64_t predict_host_submit_impl(dinoseg_t* h, const void* host_frames, c
     DSG_CUDA(h, cudaStreamWaitEvent(h->s_in, h->host_start, 0));
     int f0 = 0;
     for (int c = 0; c < nchunks; f0 += plan[c], ++c) {
-      HostLane& l = h->lanes[c % nlanes];
+      HostLane& l = h->lanes[(h->slot_seq++) % nlanes];
       const int nb = plan[c];
       if (nb <= 0) continue;
+      if (prepare_slot(l) != 0) return -1;
       // copy-in: the slot's frame staging is free once the kernels of its previous chunk have finished
       // (waiting on an event that has never been recorded is a no-op: first use of the slot)
       DSG_CUDA(h, cudaStreamWaitEvent(h->s_in, l.comp_done, 0));
@@ -1446,7 +1468,7 @@ static int predict_host_wait_impl(dinoseg_t* h, int64_t ticket) {
 
 static int predict_host_impl(dinoseg_t* h, const void* host_frames, const PreprocParams* pp, int batch,
                              uint8_t* host_lowres, int64_t* host_labels, void* stream, const char* who) {
-  const int64_t t = predict_host_submit_impl(h, host_frames, pp, batch, host_lowres, host_labels, stream, who);
+  const int64_t t = predict_host_submit_impl(h, host_frames, pp, batch, host_lowres, host_labels, stream, who, false);
   return t < 0 ? -1 : predict_host_wait_impl(h, t);
 }
 
@@ -1477,7 +1499,7 @@ int dinoseg_predict_host_u8(dinoseg_t* h, const uint8_t* host_frames, int batch,
 int64_t dinoseg_predict_host_submit(dinoseg_t* h, const float* host_frames, int batch, uint8_t* host_lowres,
                                     int64_t* host_labels, void* stream) {
   return predict_host_submit_impl(h, host_frames, nullptr, batch, host_lowres, host_labels, stream,
-                                  "dinoseg_predict_host_submit");
+                                  "dinoseg_predict_host_submit", true);
 }
 
 int64_t dinoseg_predict_host_submit_u8(dinoseg_t* h, const uint8_t* host_frames, int batch, int src_h, int src_w,
@@ -1487,7 +1509,7 @@ int64_t dinoseg_predict_host_submit_u8(dinoseg_t* h, const uint8_t* host_frames,
   PreprocParams pp;
   if (make_preproc(h, src_h, src_w, mean, std_, &pp) != 0) return -1;
   return predict_host_submit_impl(h, host_frames, &pp, batch, host_lowres, host_labels, stream,
-                                  "dinoseg_predict_host_submit_u8");
+                                  "dinoseg_predict_host_submit_u8", true);
 }
 
 int dinoseg_predict_host_wait(dinoseg_t* h, int64_t ticket) { return predict_host_wait_impl(h, ticket); }
