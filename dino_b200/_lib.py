@@ -65,8 +65,10 @@ SIGNATURES = {
                                  C.c_void_p]),
     "dinoseg_op_mlp_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p]),
-    "dinoseg_op_mlp_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "dinoseg_op_fold_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "dinoseg_op_mlp_ln": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_void_p]),
     "dinoseg_op_gemm_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "dinoseg_set_pair_kernels": (C.c_int, [C.c_void_p, C.c_int]),

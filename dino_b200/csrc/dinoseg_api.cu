@@ -324,7 +324,7 @@ cudaError_t launch_layernorm(const float* x, const float* g, const float* b, __n
                              bool split, cudaStream_t s) {
   const int rows_per_block = 8;
   dim3 grid((M + rows_per_block - 1) / rows_per_block);
-  if (D == 384 && !split) layernorm_bf16_kernel<384, false><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
+  if (D == 384 && !split) layernorm384_bf16_kernel<<<(M + 31) / 32, 256, 0, s>>>(x, g, b, y, M, eps);
   else if (D == 768 && !split) layernorm_bf16_kernel<768, false><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
   else if (D == 128 && !split) layernorm_bf16_kernel<128, false><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
   else if (D == 384 && split) layernorm_bf16_kernel<384, true><<<grid, 256, 0, s>>>(x, g, b, y, M, eps);
@@ -373,6 +373,9 @@ struct BlockW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   __nv_bfloat16 *qkv_w = nullptr, *proj_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
   float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  // fc1 as loaded (fp32): fc1_w / fc1_b above are derived from these by finalize_weights - plain bf16 / copy, or with
+  // LayerNorm2's gamma / beta folded in when the fused MLP kernel computes the LayerNorm itself
+  float *fc1_w32 = nullptr, *fc1_b32 = nullptr;
   CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
   CUtensorMap tm_fc1_g, tm_fc2_g;   // 128-row granule views for the fused MLP kernel
   CUtensorMap tm_fc1_h, tm_fc2_h;   // 64-row half granules (CTA-pair variant)
@@ -534,6 +537,8 @@ struct dinoseg {
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
   bool fuse_ln = true;              // ... which also computes LayerNorm2 itself (no LN launch, no bf16 copy of the tokens)
+  bool weights_dirty = true;        // fc1_w / fc1_b have to be (re)derived from the loaded parameters
+  bool folded = false;              // ... and currently carry LayerNorm2's gamma / beta
   int reverse_order = 1;            // GEMM / MLP kernels walk the rows last-to-first, LN / attention first-to-last
   // CTA-pair (cta_group::2) kernels: on by default (dinoseg_set_pair_kernels / DINOSEG_PAIR=0 select the single-CTA
   // forms).  Bit-identical results; +2 % on the ViT-S step, +5 % on ViT-B.  A device / partition without 2-CTA
@@ -784,13 +789,14 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     rc |= dev_alloc(h, &b.qkv_w, size_t(3) * D * D); rc |= dev_alloc(h, &b.qkv_b, 3 * D);
     rc |= dev_alloc(h, &b.proj_w, size_t(D) * D); rc |= dev_alloc(h, &b.proj_b, D);
     rc |= dev_alloc(h, &b.fc1_w, size_t(HID) * D); rc |= dev_alloc(h, &b.fc1_b, HID);
+    rc |= dev_alloc(h, &b.fc1_w32, size_t(HID) * D); rc |= dev_alloc(h, &b.fc1_b32, HID);
     rc |= dev_alloc(h, &b.fc2_w, size_t(D) * HID); rc |= dev_alloc(h, &b.fc2_b, D);
     if (rc) break;
     add_slot(h, pre + "norm1.weight", 0, b.ln1_g, {D}); add_slot(h, pre + "norm1.bias", 0, b.ln1_b, {D});
     add_slot(h, pre + "norm2.weight", 0, b.ln2_g, {D}); add_slot(h, pre + "norm2.bias", 0, b.ln2_b, {D});
     add_slot(h, pre + "attn.qkv.weight", 1, b.qkv_w, {3 * D, D}); add_slot(h, pre + "attn.qkv.bias", 0, b.qkv_b, {3 * D});
     add_slot(h, pre + "attn.proj.weight", 1, b.proj_w, {D, D}); add_slot(h, pre + "attn.proj.bias", 0, b.proj_b, {D});
-    add_slot(h, pre + "mlp.fc1.weight", 1, b.fc1_w, {HID, D}); add_slot(h, pre + "mlp.fc1.bias", 0, b.fc1_b, {HID});
+    add_slot(h, pre + "mlp.fc1.weight", 0, b.fc1_w32, {HID, D}); add_slot(h, pre + "mlp.fc1.bias", 0, b.fc1_b32, {HID});
     add_slot(h, pre + "mlp.fc2.weight", 1, b.fc2_w, {D, HID}); add_slot(h, pre + "mlp.fc2.bias", 0, b.fc2_b, {D});
     bool ok = true;
     ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, GEMM_BN);
@@ -882,6 +888,7 @@ int dinoseg_set_weight(dinoseg_t* h, const char* key, const float* dev_ptr, cons
     DSG_CUDA(h, cudaMemcpyAsync(sl.dst, dev_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   h->have.insert(key);
+  h->weights_dirty = true;          // derived operands (fc1 with or without the folded LayerNorm2) are rebuilt lazily
   return 0;
 }
 
@@ -997,6 +1004,30 @@ int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind,
   return 0;
 }
 
+// Derived operands: fc1 weight (bf16) and bias of every block, with LayerNorm2's affine transform folded in when the
+// fused MLP kernel normalises the tokens itself (fold_ln_weight_kernel), plain otherwise.  Runs when a parameter or the
+// mode changed; synchronises the stream so that forwards on other streams see the result.
+static int finalize_weights(dinoseg_t* h, cudaStream_t s) {
+  const bool fold = h->fused_mlp && h->fuse_ln;
+  if (!h->weights_dirty && h->folded == fold) return 0;
+  const int D = h->cfg.embed_dim, HID = h->cfg.mlp_hidden;
+  for (BlockW& b : h->blocks) {
+    if (fold) {
+      fold_ln_weight_kernel<<<(HID * 32 + 255) / 256, 256, 0, s>>>(b.fc1_w32, b.fc1_b32, b.ln2_g, b.ln2_b, b.fc1_w, b.fc1_b,
+                                                                   HID, D);
+    } else {
+      const size_t n = size_t(HID) * D;
+      f32_to_bf16_kernel<<<unsigned(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, s>>>(b.fc1_w32, b.fc1_w, n);
+      DSG_CUDA(h, cudaMemcpyAsync(b.fc1_b, b.fc1_b32, size_t(HID) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    DSG_CUDA(h, cudaGetLastError());
+  }
+  DSG_CUDA(h, cudaStreamSynchronize(s));
+  h->weights_dirty = false;
+  h->folded = fold;
+  return 0;
+}
+
 // Launch sequence of one forward pass over `batch` frames on the buffers of `w` (already bound).
 // `frames` are normalised fp32 NCHW frames, or (frames == nullptr) `frames_u8` raw uint8 HWC frames that are resized
 // and normalised on the fly (pp).
@@ -1011,6 +1042,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
              miss.c_str());
   }
   if ((!frames && !(frames_u8 && pp)) || batch <= 0) DSG_FAIL(h, "dinoseg_forward: bad arguments");
+  if (finalize_weights(h, s) != 0) return -1;
   if (size_t(batch) * h->Ntok > size_t(INT32_MAX) / 4) DSG_FAIL(h, "dinoseg_forward: batch too large");
   h->last = &w;
   const int D = h->cfg.embed_dim, HID = h->cfg.mlp_hidden, H = h->cfg.num_heads;
@@ -1092,7 +1124,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       MlpParams p{};
       p.M = M; p.x = w.x; p.b1 = b.fc1_b; p.b2 = b.fc2_b;
       if (h->fuse_ln) {
-        p.ln_g = b.ln2_g; p.ln_b = b.ln2_b; p.ln_eps = eps;
+        p.fuse_ln = 1; p.ln_eps = eps;             // gamma / beta are in fc1_w / fc1_b (finalize_weights)
       } else {
         LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln2_g, b.ln2_b, w.abuf, M, D, eps, false, s)); ++n;
       }
@@ -1698,6 +1730,7 @@ int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
     DSG_FAIL(h, "the fused MLP kernel needs embed_dim 384 and mlp_hidden 1536");
   h->fused_mlp = on != 0;
   h->mlp_pair = on == 2;
+  h->weights_dirty = true;          // fc1 with / without the folded LayerNorm2
   return 0;
 }
 
@@ -1724,21 +1757,29 @@ int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const f
   return launch_mlp_fused(ta, t1, t2, tx, p, sms, pair != 0, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
-int dinoseg_op_mlp_ln(float* x, const float* gamma, const float* beta, float eps, const void* W1_bf16, const float* b1,
-                      const void* W2_bf16, const float* b2, int M, int pair, void* stream) {
-  if (!x || !gamma || !beta || !W1_bf16 || !b1 || !W2_bf16 || !b2 || M <= 0) return -1;
+int dinoseg_op_fold_ln(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                       void* W_out_bf16, float* bias_out, void* stream) {
+  if (!W || !bias || !gamma || !beta || !W_out_bf16 || !bias_out || N <= 0 || K <= 0) return -1;
+  fold_ln_weight_kernel<<<(N * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, bias, gamma, beta, static_cast<__nv_bfloat16*>(W_out_bf16), bias_out, N, K);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int dinoseg_op_mlp_ln(float* x, float eps, const void* W1f_bf16, const float* b1f, const void* W2_bf16, const float* b2,
+                      int M, int pair, void* stream) {
+  if (!x || !W1f_bf16 || !b1f || !W2_bf16 || !b2 || M <= 0) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   CUtensorMap t1, t2, tx;
   const uint32_t wrows = pair ? 64 : 128;
-  bool ok = make_tmap_2d(&t1, W1_bf16, MLP_HID, MLP_D, MLP_D, wrows);
+  bool ok = make_tmap_2d(&t1, W1f_bf16, MLP_HID, MLP_D, MLP_D, wrows);
   ok &= make_tmap_2d(&t2, W2_bf16, MLP_D, MLP_HID, MLP_HID, wrows);
   ok &= make_tmap_gemm_out(&tx, x, true, MLP_D, M, 1, MLP_D);
   if (!ok) return -2;
   MlpParams p{};
-  p.M = M; p.x = x; p.b1 = b1; p.b2 = b2;
-  p.ln_g = gamma; p.ln_b = beta; p.ln_eps = eps;
+  p.M = M; p.x = x; p.b1 = b1f; p.b2 = b2;
+  p.fuse_ln = 1; p.ln_eps = eps;
   // (the A tensor map is not used by the fused-LayerNorm form; tx stands in for it)
   return launch_mlp_fused(tx, t1, t2, tx, p, sms, pair != 0, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }

@@ -221,6 +221,91 @@ __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __res
 // LayerNorm (eps inside the sqrt, biased variance; reference :114,:118,:183 with eps=1e-6 :303)
 // fp32 in -> bf16 out (the bf16 copy is the A operand of the following GEMM).  One warp per row.
 // ---------------------------------------------------------------------------------------
+// Row statistics for D = 384 with EIGHT LANES PER ROW (a warp works on four rows at once): lane `sub` of a row's group
+// holds the row's float4 number i*8 + sub, i = 0..11.  Two-pass statistics in registers, sums over the group with three
+// xor-shuffles - one shuffle instruction serves four rows, so the dependent shuffle chain per row is 6 long instead of
+// the 10 of a warp-per-row reduction (what bounds a single warp that has to normalise many rows in a row: the fused
+// LayerNorm fill of mlp.cuh, which shares this function with the LayerNorm kernel so that both produce the same bits).
+constexpr int LN384_V = 12;
+__device__ __forceinline__ void ln384_stats(const float4 (&v)[LN384_V], float eps, float& mean, float& rstd) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN384_V; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  mean = sum * (1.0f / 384.0f);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN384_V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+  sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+  sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+  sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+  rstd = rsqrtf(sq * (1.0f / 384.0f) + eps);
+}
+// normalised, affine-transformed float4 number i*8 + sub of the row -> four bf16 (two packed words)
+__device__ __forceinline__ uint2 ln384_out(const float4& v, float mean, float rstd, const float4& gm, const float4& bt) {
+  const float a = (v.x - mean) * rstd * gm.x + bt.x, b = (v.y - mean) * rstd * gm.y + bt.y;
+  const float c = (v.z - mean) * rstd * gm.z + bt.z, d = (v.w - mean) * rstd * gm.w + bt.w;
+  uint2 o;
+  o.x = pack_bf16x2(a, b);
+  o.y = pack_bf16x2(c, d);
+  return o;
+}
+
+// normalised float4 WITHOUT the affine transform (the consumer's weights carry gamma and beta: fold_ln_weight_kernel)
+__device__ __forceinline__ uint2 ln384_out_plain(const float4& v, float mean, float rstd) {
+  uint2 o;
+  o.x = pack_bf16x2((v.x - mean) * rstd, (v.y - mean) * rstd);
+  o.y = pack_bf16x2((v.z - mean) * rstd, (v.w - mean) * rstd);
+  return o;
+}
+
+// LayerNorm folded into the Linear layer that consumes it (weight-load time):
+//   Linear(LN(x)) = W (xhat * gamma + beta) + b = (W diag(gamma)) xhat + (b + W beta),   xhat = (x - mean) * rstd
+// W [N, K] fp32 -> Wf [N, K] bf16 = W * gamma (per input column), bf [N] fp32 = b + W . beta (fp32 dot).  One warp per
+// output row.  The kernel that consumes Wf then only has to produce xhat (mlp.cuh: fused LayerNorm2 -> fc1).
+__global__ void __launch_bounds__(256)
+fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ Wf, float* __restrict__ bf, int N, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* w = W + size_t(warp) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float v = w[k];
+    Wf[size_t(warp) * K + k] = __float2bfloat16_rn(v * gamma[k]);
+    acc = fmaf(v, beta[k], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) bf[warp] = b[warp] + acc;
+}
+
+// D = 384, plain bf16 output: four rows per warp (eight lanes per row), 32 rows per 256-thread block
+__global__ void __launch_bounds__(256)
+layernorm384_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         __nv_bfloat16* __restrict__ y, int M, float eps) {
+  const int sub = threadIdx.x & 7;
+  const int row = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool live = row < M;
+  const float4* xr = reinterpret_cast<const float4*>(x + size_t(live ? row : M - 1) * 384);
+  float4 v[LN384_V];
+#pragma unroll
+  for (int i = 0; i < LN384_V; ++i) v[i] = xr[i * 8 + sub];
+  float mean, rstd;
+  ln384_stats(v, eps, mean, rstd);
+  if (!live) return;
+  uint2* yr = reinterpret_cast<uint2*>(y + size_t(row) * 384);
+#pragma unroll
+  for (int i = 0; i < LN384_V; ++i)
+    yr[i * 8 + sub] = ln384_out(v[i], mean, rstd, __ldg(reinterpret_cast<const float4*>(gamma) + i * 8 + sub),
+                                __ldg(reinterpret_cast<const float4*>(beta) + i * 8 + sub));
+}
+
 // SPLIT: y is [M, 2*D] = [hi | lo] (bf16x3 operand of the head GEMM, see split_weight_kernel).
 template <int D, bool SPLIT>
 __global__ void __launch_bounds__(256)

@@ -6,10 +6,10 @@
 // hidden bias / GELU / residual passes are fused:
 //
 //   A block     : LayerNorm2(x) as bf16, resident in shared memory (6 k-blocks x 16 KB) for the 12 hidden chunks of a row
-//                 block.  Fused form (MlpParams::ln_g): the four output warps - idle between two drains - read the
-//                 block's 128 rows of x (fp32, prefetched into L2 one block ahead), normalise them exactly as the
-//                 LayerNorm kernel does and write the bf16 operand in the UMMA layout as soon as the last MMA1 of
-//                 the previous block has retired: no LayerNorm launch, no bf16 copy of the tokens in HBM.
+//                 block.  Fused form (MlpParams::fuse_ln): the four output warps - idle between two drains - read the
+//                 block's 128 rows of x (fp32, prefetched into L2 one block ahead), normalise them ((x - mean) * rstd;
+//                 gamma / beta live in W1 / b1) and write the bf16 operand in the UMMA layout as soon as the last MMA1
+//                 of the previous block has retired: no LayerNorm launch, no bf16 copy of the tokens in HBM.
 //                 Unfused form: the block is TMA-loaded from the bf16 copy the LayerNorm kernel wrote.
 //   per hidden chunk c of 128 columns (12 chunks):
 //     MMA1(c)   : acc1[128 x 128] = A . W1[c]^T              (24 MMAs 128x128x16, W1 granules via TMA)
@@ -27,6 +27,7 @@
 // (bytes in flight against the L2 latency) is what bounds the kernel: it is as deep as shared memory allows.
 #pragma once
 #include "gemm.cuh"
+#include "kernels.cuh"
 
 namespace dsg {
 
@@ -36,10 +37,10 @@ struct MlpParams {
   const float* b1;            // [1536]
   const float* b2;            // [384]
   int reverse;                // 1: row blocks are processed last to first
-  // fused LayerNorm2 (reference vision_transformer.py:118, :135): when ln_g != nullptr the A block is not TMA-loaded
-  // from a bf16 copy written by the LayerNorm kernel but produced in place from x by the output warps
-  const float* ln_g;          // [384] or nullptr
-  const float* ln_b;          // [384]
+  // fused LayerNorm2 (reference vision_transformer.py:118, :135): with fuse_ln the A block is not TMA-loaded from a bf16
+  // copy written by the LayerNorm kernel but produced in place from x by the output warps as xhat = (x - mean) * rstd;
+  // gamma and beta are folded into W1 / b1 at weight-load time (fold_ln_weight_kernel)
+  int fuse_ln;
   float ln_eps;
   long long* timing;          // debug (DSG_MLP_TIMING): [grid][2 roles][8] cycle totals
   int* hb;                    // diagnostic heartbeat (see hb_mark), may be null
@@ -166,7 +167,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < RING; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a_full, p.ln_g != nullptr ? 4 * NCTA : 1);   // fused LayerNorm: one arrival per output warp (both CTAs)
+    mbar_init(a_full, p.fuse_ln ? 4 * NCTA : 1);   // fused LayerNorm: one arrival per output warp (both CTAs)
     mbar_init(a_empty, 1);
     mbar_init(acc1_full, 1);
     mbar_init(acc1_empty, 8 * NCTA);
@@ -248,7 +249,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < MLP_KB; ++kb) tma_load_3d(sA + size_t(kb) * MLP_GRAN, &tmA, a_full, kb * 64, r0, 0);
         }
       };
-      const bool tma_a = p.ln_g == nullptr;      // fused LayerNorm: the output warps produce A
+      const bool tma_a = !p.fuse_ln;             // fused LayerNorm: the output warps produce A
       if (my_blocks > 0 && tma_a) load_a(0);
       for (int bi = 0; bi < my_blocks; ++bi) {
         for (int i = 0; i < MLP_NCH + MLP_LAG; ++i) {
@@ -462,12 +463,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int NCH = MLP_D / 32;                 // 12
     uint32_t addc = 0;                              // staging chunks so far
     // ---- fused LayerNorm2: A block of row block bi from x ----
-    // Warp w of the four takes rows w*32 .. w*32+31, four rows at a time; a row is read as three float4 per lane
-    // (columns i*128 + lane*4 ..+3, the access pattern and the arithmetic of layernorm_bf16_kernel: two-pass statistics
-    // in registers, xor-shuffle sums), normalised, rounded to bf16 and written into the k-block slots of sA in the
+    // Warp w of the four takes rows w*32 .. w*32+31, four rows per pass with the statistics of the LayerNorm kernel
+    // (ln384_stats in kernels.cuh), and writes xhat = (x - mean) * rstd as bf16 into the k-block slots of sA in the
     // K-major SWIZZLE_128B layout the TMA load would have produced: column c of row r -> slot c/64, byte
     // r*128 + (((c%64)/8 ^ (r&7)) << 4) + (c%8)*2.  Rows >= M are written as zeros (what TMA's fill does).
-    const bool fuse_ln = p.ln_g != nullptr;
+    const bool fuse_ln = p.fuse_ln != 0;
     const int ow = warp - 10;                       // 0..3
     auto prefetch_block = [&](int bi) {             // the block's 128 rows of x -> L2 (192 KB: 12 lines per thread)
       const int r0 = block_row0(bi);
@@ -476,66 +476,42 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (size_t off = size_t(threadIdx.x - 320) * 128; off < bytes; off += 128 * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
     };
-    // rows r0 + ow*32 + rb .. +3 of x into registers (three float4 per lane and row)
-    auto ln_load = [&](float4 (&v)[4][3], int r0, int rb) {
+    // Eight lanes per row, four rows per pass (ln384_stats): lane `sub` of group `grp` holds float4 number i*8 + sub of
+    // row ow*32 + pass*4 + grp, i.e. columns (i*8 + sub)*4 ..+3 -> k-block i/2, 16-byte chunk ((i&1)*8 + sub)/2 of the
+    // row's 128 bytes, 8-byte half sub&1.
+    const int sub = lane & 7, grp = lane >> 3;
+    auto ln_load = [&](float4 (&v)[LN384_V], int r0, int pass) {
+      const int row = r0 + ow * 32 + pass * 4 + grp;
+      const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(row < p.M ? row : 0) * MLP_D);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = r0 + ow * 32 + rb + q;
-        const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(row) * MLP_D);
+      for (int i = 0; i < LN384_V; ++i) v[i] = row < p.M ? __ldg(xr + i * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto ln_store = [&](const float4 (&v)[LN384_V], int r0, int pass) {
+      const int r = ow * 32 + pass * 4 + grp;       // row inside the block
+      float mean, rstd;
+      ln384_stats(v, p.ln_eps, mean, rstd);
+      const bool live = r0 + r < p.M;
+      uint8_t* rowp = sA + r * 128 + (sub & 1) * 8;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) v[q][i] = row < p.M ? __ldg(xr + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < LN384_V; ++i) {
+        uint2 o = ln384_out_plain(v[i], mean, rstd);
+        if (!live) o = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(rowp + size_t(i >> 1) * MLP_GRAN + (((((i & 1) * 8 + sub) >> 1) ^ (r & 7)) << 4)) = o;
       }
     };
-    // normalise four rows and write them into sA (gamma / beta come from L1: keeping them in registers would cost 24)
-    auto ln_store = [&](const float4 (&v)[4][3], int r0, int rb) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = ow * 32 + rb + q;             // row inside the block
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) sum += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * (1.0f / MLP_D);
-        float sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
-          sq += (a * a + b * b) + (c * c + d * d);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float rstd = rsqrtf(sq * (1.0f / MLP_D) + p.ln_eps);
-        const bool live = r0 + r < p.M;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g) + i * 32 + lane);
-          const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i * 32 + lane);
-          const float a = (v[q][i].x - mean) * rstd * gm.x + bt.x, b = (v[q][i].y - mean) * rstd * gm.y + bt.y;
-          const float c = (v[q][i].z - mean) * rstd * gm.z + bt.z, d = (v[q][i].w - mean) * rstd * gm.w + bt.w;
-          uint2 o;
-          o.x = live ? pack_bf16x2(a, b) : 0u;
-          o.y = live ? pack_bf16x2(c, d) : 0u;
-          // columns i*128 + lane*4 .. +3: k-block 2i + lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
-          uint8_t* dst = sA + size_t(2 * i + (lane >> 4)) * MLP_GRAN + r * 128 + ((((lane & 15) >> 1) ^ (r & 7)) << 4) +
-                         (lane & 1) * 8;
-          *reinterpret_cast<uint2*>(dst) = o;
-        }
-      }
-    };
-    // The fill is latency-bound (a row is 1.5 KB spread over L2 slices), so the loads run one batch of four rows ahead
-    // of the arithmetic, and the first batch is requested before the wait for the A buffer.
+    // The loads run one pass (four rows, 6 KB per warp) ahead of the arithmetic, and the first pass is requested before
+    // the wait for the A buffer.
     auto ln_fill = [&](int bi) {
       const int r0 = block_row0(bi);
-      float4 va[4][3], vb[4][3];
+      float4 va[LN384_V], vb[LN384_V];
       ln_load(va, r0, 0);
       if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1); // the last MMA1 of the previous block has read A
 #pragma unroll 1
-      for (int rb = 0; rb < 32; rb += 8) {
-        ln_load(vb, r0, rb + 4);
-        ln_store(va, r0, rb);
-        if (rb + 8 < 32) ln_load(va, r0, rb + 8);
-        ln_store(vb, r0, rb + 4);
+      for (int pass = 0; pass < 8; pass += 2) {
+        ln_load(vb, r0, pass + 1);
+        ln_store(va, r0, pass);
+        if (pass + 2 < 8) ln_load(va, r0, pass + 2);
+        ln_store(vb, r0, pass + 1);
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the UMMA reads of sA
       __syncwarp();

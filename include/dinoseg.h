@@ -204,10 +204,16 @@ int dinoseg_op_mlp(float* x, const void* A_bf16, const void* W1_bf16, const floa
 /* the same kernel run by CTA pairs (tcgen05 cta_group::2, M = 256 per MMA, weights split between the two SMs) when pair != 0 */
 int dinoseg_op_mlp_ex(float* x, const void* A_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                       const float* b2, int M, int pair, void* stream);
-/* x[M,384] fp32 (in place) += fc2(gelu(fc1(LayerNorm(x; gamma, beta, eps)))): the fused MLP kernel in the form the
- * forward uses, computing LayerNorm2 itself from the fp32 residual stream (vision_transformer.py:118, :135) */
-int dinoseg_op_mlp_ln(float* x, const float* gamma, const float* beta, float eps, const void* W1_bf16, const float* b1,
-                      const void* W2_bf16, const float* b2, int M, int pair, void* stream);
+/* LayerNorm folded into the Linear layer that consumes it: W [N,K] fp32, bias [N], gamma / beta [K] ->
+ * W_out bf16 = W * gamma (per input column), bias_out = bias + W . beta.  Linear(LN(x)) = W_out xhat + bias_out with
+ * xhat = (x - mean) * rstd: how the fused MLP kernel gets LayerNorm2's affine transform (vision_transformer.py:118). */
+int dinoseg_op_fold_ln(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                       void* W_out_bf16, float* bias_out, void* stream);
+/* x[M,384] fp32 (in place) += fc2(gelu(fc1'(xhat(x)))): the fused MLP kernel in the form the forward uses, normalising
+ * the fp32 residual stream itself; W1f / b1f carry LayerNorm2's gamma / beta (dinoseg_op_fold_ln)
+ * (vision_transformer.py:118, :135) */
+int dinoseg_op_mlp_ln(float* x, float eps, const void* W1f_bf16, const float* b1f, const void* W2_bf16, const float* b2,
+                      int M, int pair, void* stream);
 /* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel, one CTA per row block; 2: fused MLP kernel run by CTA pairs
  * (cta_group::2); 2 is the default where the fused kernel applies (embed_dim 384, mlp_hidden 1536) */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);

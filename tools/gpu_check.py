@@ -185,8 +185,9 @@ def check_mlp(name, M, pair=0):
 
 
 def check_mlp_ln(name, M, pair=0):
-    """The fused MLP kernel computing LayerNorm2 itself (dinoseg_op_mlp_ln) must reproduce, BIT FOR BIT, the LayerNorm
-    kernel followed by the same MLP kernel on its bf16 output (same arithmetic, same operand bytes), and match fp32 torch."""
+    """The fused MLP kernel normalising the residual stream itself, with LayerNorm2's gamma / beta folded into fc1
+    (dinoseg_op_fold_ln + dinoseg_op_mlp_ln), against fp32 torch and against the two-kernel path (LayerNorm kernel, then the
+    MLP kernel on its bf16 output): same function, operands rounded to bf16 at different points."""
     torch, L, lib = _imports()
     torch.manual_seed(8)
     dev = "cuda"
@@ -194,27 +195,30 @@ def check_mlp_ln(name, M, pair=0):
     x[3] *= 40.0                                   # a row with a large mean / spread
     g = 1.0 + 0.1 * torch.randn(384, device=dev)
     b = 0.1 * torch.randn(384, device=dev)
-    W1 = (torch.randn(1536, 384, device=dev) * 0.05).to(torch.bfloat16)
+    W1 = torch.randn(1536, 384, device=dev) * 0.05
     b1 = 0.1 * torch.randn(1536, device=dev)
     W2 = (torch.randn(384, 1536, device=dev) * 0.03).to(torch.bfloat16)
     b2 = 0.1 * torch.randn(384, device=dev)
     F = torch.nn.functional
-    ln = F.layer_norm(x, (384,), g, b, 1e-6)
-    hid = F.gelu(F.linear(ln.to(torch.bfloat16).float(), W1.float(), b1))
-    ref = x + F.linear(hid.to(torch.bfloat16).float(), W2.float(), b2)
+    ref = x + F.linear(F.gelu(F.linear(F.layer_norm(x, (384,), g, b, 1e-6), W1, b1)), W2.float(), b2)     # fp32 throughout
     A = torch.zeros(M, 384, device=dev, dtype=torch.bfloat16)
     rc0 = lib.dinoseg_op_layernorm(_ptr(x), _ptr(g), _ptr(b), _ptr(A), M, 384, 1e-6, None)
     two = x.clone()
-    rc1 = lib.dinoseg_op_mlp_ex(_ptr(two), _ptr(A), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, pair, None)
+    W1b = W1.to(torch.bfloat16)
+    rc1 = lib.dinoseg_op_mlp_ex(_ptr(two), _ptr(A), _ptr(W1b), _ptr(b1), _ptr(W2), _ptr(b2), M, pair, None)
+    W1f = torch.zeros(1536, 384, device=dev, dtype=torch.bfloat16)
+    b1f = torch.zeros(1536, device=dev)
+    rc2 = lib.dinoseg_op_fold_ln(_ptr(W1), _ptr(b1), _ptr(g), _ptr(b), 1536, 384, _ptr(W1f), _ptr(b1f), None)
     one = x.clone()
-    rc2 = lib.dinoseg_op_mlp_ln(_ptr(one), _ptr(g), _ptr(b), 1e-6, _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), M, pair, None)
+    rc3 = lib.dinoseg_op_mlp_ln(_ptr(one), 1e-6, _ptr(W1f), _ptr(b1f), _ptr(W2), _ptr(b2), M, pair, None)
     torch.cuda.synchronize()
-    err = (one - ref).abs().max().item()
-    scale = ref.abs().max().item()
-    same = bool(torch.equal(one, two))
-    return _report(name, rc0 == 0 and rc1 == 0 and rc2 == 0 and same and err <= 1e-2 * scale and bool(torch.isfinite(one).all()),
-                   rc=[rc0, rc1, rc2], identical_to_ln_kernel_plus_mlp=same, max_abs_err=err, ref_absmax=scale,
-                   max_diff_vs_two_kernels=(one - two).abs().max().item())
+    fold_ok = bool(torch.equal(W1f, (W1 * g).to(torch.bfloat16))) and (b1f - (b1 + W1 @ b)).abs().max().item() <= 1e-5
+    scale = (ref - x).abs().max().item()           # size of the MLP update (x itself is added exactly)
+    err1, err2 = (one - ref).abs().max().item(), (two - ref).abs().max().item()
+    ok = rc0 == 0 and rc1 == 0 and rc2 == 0 and rc3 == 0 and fold_ok and err1 <= 1e-2 * scale and err2 <= 1e-2 * scale \
+        and bool(torch.isfinite(one).all())
+    return _report(name, ok, rc=[rc0, rc1, rc2, rc3], fold_exact=fold_ok, max_abs_err_fused=err1, max_abs_err_two_kernels=err2,
+                   update_absmax=scale, max_diff_fused_vs_two_kernels=(one - two).abs().max().item())
 
 
 def check_layernorm(name, M, D):
