@@ -77,7 +77,8 @@ constexpr int MLP_GRAN = 128 * 64 * 2;              // 16 KB
 constexpr int MLP_RING = 4;
 constexpr int MLP_LAG = 1;                          // MMA2(c) is issued right after MMA1(c + MLP_LAG) (a lag of 2 measured 25 % slower: single G buffer)
 constexpr int MLP_THREADS = 64 + 256 + 128;         // producer + MMA, 8 GELU warps, 4 output warps
-constexpr size_t MLP_SMEM = size_t(MLP_KB) * MLP_GRAN + 2 * MLP_GRAN + 2 * MLP_GRAN + size_t(MLP_RING) * MLP_GRAN + 1024 + 512;
+constexpr size_t MLP_SMEM = size_t(MLP_KB) * MLP_GRAN + 2 * MLP_GRAN + 2 * MLP_GRAN + size_t(MLP_RING) * MLP_GRAN + 1024 + 512 +
+                            MLP_BM * sizeof(float2);   // + barriers (512) + LayerNorm statistics of the next row block (1 KB)
 
 // gelu(x) = 0.5 x + |x| (0.5 - Phi(-|x|)),  Phi(-|x|) = 2^-(q(|x|) + 1)   (same polynomial q as gelu_erf, evaluated
 // for two values at once with packed fp32x2 FMAs: 9 FMA-pipe + 4 ALU + 2 MUFU instructions per pair)
@@ -136,6 +137,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc2_full = g_empty + 1;                // 1 (commit after the last MMA2)
   uint64_t* acc2_empty = acc2_full + 1;             // 1 (4 arrivals per CTA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  float2* sStats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [128] (mean, rstd) per row
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -486,25 +488,44 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < LN384_V; ++i) v[i] = row < p.M ? __ldg(xr + i * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    // Two phases.  (1) Statistics: any time before the A buffer frees up - while the MMAs of the current block run and
+    // these warps have nothing else to do - the block's rows are read once (HBM -> L2 -> registers), mean and rstd of
+    // each row go to shared memory (1 KB).  (2) Write: once the last MMA1 of the previous block has retired, the rows are
+    // read again (L2 hits), normalised with the stored statistics and written into sA.  Phase 2 is what the tensor pipe
+    // may have to wait for, and it is pure streaming: no reductions, no shuffles, loads one pass ahead.
+    auto ln_stats_pass = [&](int bi) {
+      const int r0 = block_row0(bi);
+      float4 va[LN384_V], vb[LN384_V];
+      ln_load(va, r0, 0);
+#pragma unroll 1
+      for (int pass = 0; pass < 8; pass += 2) {
+        ln_load(vb, r0, pass + 1);
+        float mean, rstd;
+        ln384_stats(va, p.ln_eps, mean, rstd);
+        if (sub == 0) sStats[ow * 32 + pass * 4 + grp] = make_float2(mean, rstd);
+        if (pass + 2 < 8) ln_load(va, r0, pass + 2);
+        ln384_stats(vb, p.ln_eps, mean, rstd);
+        if (sub == 0) sStats[ow * 32 + (pass + 1) * 4 + grp] = make_float2(mean, rstd);
+      }
+      __syncwarp();                                 // the statistics are read back by the lanes of this warp only
+    };
     auto ln_store = [&](const float4 (&v)[LN384_V], int r0, int pass) {
       const int r = ow * 32 + pass * 4 + grp;       // row inside the block
-      float mean, rstd;
-      ln384_stats(v, p.ln_eps, mean, rstd);
+      const float2 st = sStats[r];
       const bool live = r0 + r < p.M;
       uint8_t* rowp = sA + r * 128 + (sub & 1) * 8;
 #pragma unroll
       for (int i = 0; i < LN384_V; ++i) {
-        uint2 o = ln384_out_plain(v[i], mean, rstd);
+        uint2 o = ln384_out_plain(v[i], st.x, st.y);
         if (!live) o = make_uint2(0u, 0u);
         *reinterpret_cast<uint2*>(rowp + size_t(i >> 1) * MLP_GRAN + (((((i & 1) * 8 + sub) >> 1) ^ (r & 7)) << 4)) = o;
       }
     };
-    // The loads run one pass (four rows, 6 KB per warp) ahead of the arithmetic, and the first pass is requested before
-    // the wait for the A buffer.
     auto ln_fill = [&](int bi) {
       const int r0 = block_row0(bi);
+      ln_stats_pass(bi);
       float4 va[LN384_V], vb[LN384_V];
-      ln_load(va, r0, 0);
+      ln_load(va, r0, 0);                           // (requested before the wait for the A buffer)
       if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1); // the last MMA1 of the previous block has read A
 #pragma unroll 1
       for (int pass = 0; pass < 8; pass += 2) {
