@@ -475,8 +475,8 @@ def main():
                "h2d_bytes_per_step": int(frames_host.numel() * 4 * world),
                "d2h_bytes_per_step": d2h, "host_label_bytes_per_step": int(out.size * 8 * world),
                "api": "DINOSeg.predict_batch_async / predict_wait (pinned host fp32 frames -> int64 host label maps; "
-                      "dinoseg_predict_host_submit / _wait: H2D + forward + D2H inside the timed region, pipelined over "
-                      "~10-frame chunks on 3 streams, two steps in flight; " + tail + ")"}
+                      "dinoseg_predict_host_submit / _wait: H2D + forward + D2H inside the timed region on the library's "
+                      "copy-in / compute / copy-out streams, two steps in flight; " + tail + ")"}
         # ---- the same from RAW camera frames (uint8 640x480 RGB, as DINOSeg.predict receives them): resize + normalise
         # on the GPU as well; informational, the contract's `e2e` is the fp32 path above ----
         if res == 480:

@@ -15,7 +15,7 @@
 // kernel is persistent (grid = #SMs, item = blockIdx.x + k*gridDim.x) and streams the 128-key K/V
 // tiles of the item through a shared-memory ring.
 //
-// Warp roles (384 threads, 1 CTA/SM, all 512 TMEM columns):
+// Warp roles (640 threads, 1 CTA/SM, all 512 TMEM columns):
 //   warp 0      : TMA producer (Q pair per item; K,V ring)
 //   warps 1, 2  : one tcgen05.mma-issuing thread per query tile (warp 1 also allocates TMEM)
 //                   S_t = Q_t K^T          (SS, both K-major)            t = 0,1
@@ -25,12 +25,12 @@
 //                 (s_empty), long before P_t(j) exists: the softmax warps never wait for the tensor
 //                 pipe.  Issue order per key tile j:  QK0(j+1) QK1(j+1) PV0(j) PV1(j).
 //   warp 3      : idle (it only completes the producer warpgroup for setmaxnreg)
-//   softmax warps, SMW per query tile (template parameter):
-//     SMW = 4 (384 threads): warps 4..7 / 8..11, one query row per thread (tcgen05.ld 32x32b), 128 scores per thread
-//     SMW = 8 (640 threads): warps 4..11 / 12..19, each warp owns 16 rows and reads them in the 16x256b accumulator-
-//                 fragment layout: a row lives in one quad (32 of its 128 scores per thread, two rows per thread), the
-//                 row max is two quad shuffles.  Four softmax warps per scheduler instead of two: the tcgen05.ld /
-//                 row-max / barrier phases of one warp hide under the exponentials of the other three.
+//   warps 4..11 / 12..19: softmax of query tile 0 / 1 (640 threads in all).  Each warp owns 16 rows and reads them in
+//                 the 16x256b accumulator-fragment layout: a row lives in one quad (32 of its 128 scores per thread,
+//                 two rows per thread), the row max is two quad shuffles.  Four softmax warps per scheduler: the
+//                 tcgen05.ld / row-max / barrier phases of one warp hide under the exponentials of the other three.
+//                 (Round 1 used one row per thread, 128 scores per thread, two warps per scheduler: 1.51 ms per
+//                 launch against 1.39 ms)
 // The exponentials are the bottleneck at head_dim 64 (16 MUFU.EX2 per clock per SM vs 8192 tensor
 // flop per clock; 2*128*128 exps per key tile = 2048 MUFU clocks vs 1354 clocks of MMA):
 //   * a quarter of the exponentials is evaluated with a degree-3 polynomial on the FMA/ALU pipes
@@ -65,17 +65,16 @@ struct AttnParams {
 constexpr int ATT_BM = 128;     // queries per tile (two tiles per work item)
 constexpr int ATT_BN = 128;     // keys per tile
 constexpr int ATT_DH = 64;      // head dim
-constexpr int att_threads(int smw) { return 128 + 64 * smw; }   // producer warpgroup + 2 query tiles x SMW warps
-// bit i: pair i of every 16-pair chunk uses the polynomial exp2 instead of MUFU.EX2.  The best share depends on the
-// softmax form: with one row per thread (two softmax warps per scheduler) a quarter of the pairs (1.606 / 1.540 /
-// 1.512 / 1.593 ms at 0 / 12.5 / 25 / 31 %); with 16-row warps (four per scheduler) the kernel is no longer bound by
-// the exponentials alone but also by its instruction issue, and every polynomial pair costs 15 instructions against
-// 5: an eighth (1.446 / 1.397 / 1.441 / 1.520 ms at 0 / 12.5 / 25 / 37.5 %).
-#ifdef DSG_ATTN_POLY_MASK
-constexpr unsigned ATT_POLY_MASK_ROWS = DSG_ATTN_POLY_MASK, ATT_POLY_MASK_QUADS = DSG_ATTN_POLY_MASK;
-#else
-constexpr unsigned ATT_POLY_MASK_ROWS = 0x8888, ATT_POLY_MASK_QUADS = 0x8080;
+constexpr int ATT_SMW = 8;                                  // softmax warps per query tile
+constexpr int ATT_THREADS = 128 + 2 * 32 * ATT_SMW;         // producer warpgroup + 2 query tiles x 8 warps = 640
+// bit i: pair i of every 16-pair chunk uses the polynomial exp2 instead of MUFU.EX2.  With four softmax warps per
+// scheduler the kernel is bound by the exponentials AND by its instruction issue, and a polynomial pair costs 13
+// instructions against 5: an eighth of the pairs is the optimum (1.437 / 1.404 / 1.390 / 1.399 / 1.425 / 1.520 ms per
+// launch at 0 / 6 / 12.5 / 19 / 25 / 37.5 %; round 1's one-row-per-thread form, two warps per scheduler, wanted 25 %).
+#ifndef DSG_ATTN_POLY_MASK
+#define DSG_ATTN_POLY_MASK 0x8080
 #endif
+constexpr unsigned ATT_POLY_MASK_QUADS = DSG_ATTN_POLY_MASK;
 constexpr int ATT_TILE_BYTES = 128 * ATT_DH * 2;  // 16 KB (Q, K or V tile)
 
 // Work items.  A regular item is a PAIR of 128-query tiles of one (frame, head): both warpgroups share one K/V
@@ -124,9 +123,8 @@ __host__ __device__ __forceinline__ AttItem att_decode(const AttnParams& p, int 
   return I;
 }
 
-// s_empty / p_full take one arrival per softmax THREAD: one arrival per warp (__syncwarp + elected lane) measured 6 %
-// slower for the whole kernel (1.60 vs 1.50 ms) - the extra convergence point costs more than the 124 arrivals.
-__device__ __forceinline__ void att_arrive(uint64_t* bar, int) { mbar_arrive(bar); }
+// (s_empty / p_full take one arrival per softmax THREAD: one arrival per warp - __syncwarp + elected lane - measured 6 %
+// slower for the whole kernel: the extra convergence point costs more than the arrivals it saves.)
 
 template <int KV_STAGES>
 constexpr size_t attn_smem_bytes() {
@@ -142,7 +140,7 @@ constexpr uint32_t ATT_T_COLS = 256, ATT_S_OFF = 0, ATT_P_OFF = 128, ATT_O_OFF =
 constexpr float ATT_LOG2E = 1.4426950408889634f;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays <= 2^8
 
-// register split of the 640-thread form (see the setmaxnreg comment in the kernel): 128 * producer + 512 * softmax <= 61440
+// register split (see the setmaxnreg comment in the kernel): 128 * producer + 512 * softmax <= 61440
 #ifndef DSG_ATT_QUAD_SOFTMAX_REGS
 #define DSG_ATT_QUAD_SOFTMAX_REGS 104
 #define DSG_ATT_QUAD_PRODUCER_REGS 56
@@ -161,172 +159,7 @@ __device__ __forceinline__ float2 att_exp_pair(float s0, float s1, float2 l2e, f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// softmax, one query row per thread (SMW = 4: warps 4..7 query tile 0, 8..11 query tile 1)
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void att_softmax_rows(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
-                                                 const int warp, const int lane, const int num_tiles) {
-  constexpr float LOG2E = ATT_LOG2E, RESCALE_THRESHOLD = ATT_RESCALE_THRESHOLD;
-  uint64_t* const s_full = bars.s_full; uint64_t* const s_empty = bars.s_empty;
-  uint64_t* const p_full = bars.p_full; uint64_t* const pv_done = bars.pv_done;
-  {
-    const int t = (warp - 4) >> 2;                 // query tile of this warpgroup
-    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
-    const uint32_t s_addr = lane_base + uint32_t(t) * ATT_T_COLS + ATT_S_OFF;
-    const uint32_t o_addr = lane_base + uint32_t(t) * ATT_T_COLS + ATT_O_OFF;
-    const uint32_t p_addr = lane_base + uint32_t(t) * ATT_T_COLS + ATT_P_OFF;
-    uint32_t sc = 0;                               // key tiles processed so far by this warpgroup
-#ifdef DSG_ATTN_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-#endif
-
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const AttItem I = att_decode(p, item);
-      if (t == 1 && !I.act1) continue;             // unpaired tail item
-      const int bh = t ? I.bh[1] : I.bh[0];      // (no dynamic indexing: keeps the struct in registers)
-      const int h = bh % p.H, b = bh / p.H;
-      const int q0 = t ? I.q0[1] : I.q0[0];
-      float m = 0.f;                               // (stale) running row max of the raw scores
-      float l = 0.f;                               // running row sum of exp(s - m)
-
-      for (int j = 0; j < num_tiles; ++j, ++sc) {
-        ATT_T(7);
-        mbar_wait(&s_full[t], sc & 1);
-        tc_fence_after();
-        ATT_T(0);
-        float s[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(s_addr + uint32_t(c * 32), r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
-        }
-        tmem_ld_wait();
-        ATT_T(1);
-        tc_fence_before();
-        att_arrive(&s_empty[t], lane);             // the tensor pipe may overwrite S_t with the next scores
-        const int kbase = j * ATT_BN;
-        if (kbase + ATT_BN > p.N) {
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (kbase + i >= p.N) s[i] = -INFINITY;
-        }
-        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
-#pragma unroll
-        for (int i = 8; i < 128; i += 8) {
-          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1])); mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
-          mx2 = fmaxf(mx2, fmaxf(s[i + 4], s[i + 5])); mx3 = fmaxf(mx3, fmaxf(s[i + 6], s[i + 7]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        ATT_T(2);
-        if (j == 0) {
-          m = mx;                                  // first PV overwrites O (accumulate = 0)
-        } else {
-          // PV_t(j-1) must have retired before P_t is overwritten or O_t is rescaled.  (Deferring this wait until
-          // the first 32 exponentials are done, or testing the barrier early and skipping the wait, both measured
-          // 3-4 % slower: the extra branch in the unrolled exp loop costs more than the stall it hides.)
-          mbar_wait(&pv_done[t], (sc - 1) & 1);
-          tc_fence_after();
-          ATT_T(3);
-          const bool grow = (mx - m) * LOG2E > RESCALE_THRESHOLD;
-          if (__any_sync(0xffffffffu, grow)) {
-            const float m_new = grow ? mx : m;
-            const float alpha = fast_exp2((m - m_new) * LOG2E);   // 1 for the rows that keep their max
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld_x32(o_addr + uint32_t(c * 32), r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st_x32(o_addr + uint32_t(c * 32), r);
-            }
-            l *= alpha;
-            m = m_new;
-          }
-        }
-        const float2 nmb = make_float2(-m * LOG2E, -m * LOG2E);
-        const float2 l2e = make_float2(LOG2E, LOG2E);
-        float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
-        ATT_T(4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 x = ffma2(make_float2(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), l2e, nmb);
-#ifdef DSG_EXP_NO_MUFU
-            const float2 e = x;
-#else
-            // a fixed share of the pairs is evaluated on the FMA/ALU pipes (exp2_poly_x2), the rest on MUFU
-            const float2 e = ((ATT_POLY_MASK_ROWS >> i) & 1) ? exp2_poly_x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
-#endif
-#ifndef DSG_EXP_NO_SUM
-            if (i & 1) sum23 = fadd2(sum23, e); else sum01 = fadd2(sum01, e);
-#else
-            sum01.x = e.x;
-#endif
-#ifndef DSG_EXP_NO_PACK
-            pk[i] = pack_bf16x2(e.x, e.y);
-#else
-            pk[i] = __float_as_uint(e.x) ^ __float_as_uint(e.y);
-#endif
-          }
-#ifndef DSG_EXP_NO_ST
-          tmem_st_x16(p_addr + uint32_t(c * 16), pk);
-#else
-          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u && pk[15] == pk[3]) tmem_st_x16(p_addr + uint32_t(c * 16), pk);
-#endif
-        }
-        ATT_T(5);
-        l += (sum01.x + sum01.y) + (sum23.x + sum23.y);
-        tmem_st_wait();
-        tc_fence_before();
-        att_arrive(&p_full[t], lane);
-        ATT_T(6);
-      }
-
-      // epilogue: O / l -> bf16 -> out[b*N + q, h*64 + d]
-      mbar_wait(&pv_done[t], (sc - 1) & 1);
-      tc_fence_after();
-      const float inv_l = 1.0f / l;
-      const int q = q0 + row;
-      __nv_bfloat16* o = p.out + (size_t(b) * p.N + q) * p.D + h * ATT_DH;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld_x32(o_addr + uint32_t(c * 32), r);
-        tmem_ld_wait();
-        if (q < p.N) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-            v.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-            v.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-            v.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(o + c * 32 + i) = v;
-          }
-        }
-      }
-      // O_t is free again once every thread's tcgen05.ld has completed (wait::ld above); the next
-      // item's first PV_t is ordered after this warpgroup's next p_full arrival.
-      tc_fence_before();
-    }
-#ifdef DSG_ATTN_TIMING
-    if (p.timing != nullptr && (threadIdx.x & 127) == 0) {
-      for (int i = 0; i < 8; ++i) p.timing[(size_t(blockIdx.x) * 2 + t) * 8 + i] = tacc[i];
-    }
-#endif
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// softmax, 16 rows per warp in the accumulator-fragment layout (SMW = 8: warps 4..11 query tile 0, 12..19 tile 1).
+// softmax, 16 rows per warp in the accumulator-fragment layout (warps 4..11 query tile 0, 12..19 tile 1).
 // Warp w serves TMEM lanes 32*(w%4) + 16*((w-4)/4 % 2) .. +15.  Thread (r = lane/4, q = lane%4) holds rows r and r+8 of
 // those 16 and, of every 8-key group k, the keys 8k + 2q, 8k + 2q + 1: 64 scores per key tile instead of 128, and
 // twice as many warps per scheduler to overlap the load / max / barrier phases with the exponentials.
@@ -467,12 +300,11 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
   }
 }
 
-template <int KV_STAGES, int SMW>
-__global__ void __launch_bounds__(att_threads(SMW), 1)
+template <int KV_STAGES>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  static_assert(SMW == 4 || SMW == 8, "softmax warps per query tile");
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t ATT_ARRIVALS = 32 * SMW;    // s_empty / p_full: one arrival per softmax thread of the query tile
+  constexpr uint32_t ATT_ARRIVALS = 32 * ATT_SMW;   // s_empty / p_full: one arrival per softmax thread of the query tile
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -494,7 +326,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int lane = threadIdx.x & 31;
   const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
 
-  constexpr int HB_CODE = 300 + SMW;
+  constexpr int HB_CODE = 300 + ATT_SMW;
   hb_mark(p.hb, HB_CODE, 1);
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQKV);
@@ -521,9 +353,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
   if (warp < 4) {
     // Registers move from the producer warpgroup to the softmax warps.  The budget is the CTA's register pool AT LAUNCH
-    // (threads x the kernel's register count), not the SM's 64 K: 384 x 168 = 64512 >= 128*80 + 256*208 (SMW = 4);
-    // 640 x 96 = 61440 >= 128*56 + 512*104 (SMW = 8).  A setmaxnreg.inc beyond the pool blocks forever.
-    if constexpr (SMW == 4) setmaxnreg_dec<80>(); else setmaxnreg_dec<ATT_QUAD_PRODUCER_REGS>();
+    // (threads x the kernel's register count: 640 x 96 = 61440 >= 128*56 + 512*104), not the SM's 64 K: a
+    // setmaxnreg.inc beyond the pool blocks for ever.
+    setmaxnreg_dec<ATT_QUAD_PRODUCER_REGS>();
     if (warp == 0 && elect_one()) {
       // ------------------------------ TMA producer ------------------------------
       uint32_t kvc = 0;
@@ -637,13 +469,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   } else {
     // ------------------------------ softmax warps ------------------------------
     const AttBars ab{s_full, s_empty, p_full, pv_done};
-    if constexpr (SMW == 4) {
-      setmaxnreg_inc<208>();
-      att_softmax_rows(p, tmem_base, ab, warp, lane, num_tiles);
-    } else {
-      setmaxnreg_inc<ATT_QUAD_SOFTMAX_REGS>();
-      att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
-    }
+    setmaxnreg_inc<ATT_QUAD_SOFTMAX_REGS>();
+    att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
   }
 
   hb_mark(p.hb, HB_CODE, 3);

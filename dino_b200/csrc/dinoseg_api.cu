@@ -286,19 +286,11 @@ void attn_plan_items(AttnParams& p) {
   p.num_items = p.B * p.H * p.full_pairs + (p.lone ? (p.B * p.H + 1) / 2 : 0);
 }
 
-// softmax warps per query tile: 8 (16-row warps in the accumulator-fragment layout, 640 threads) or 4 (one row per
-// thread, 384 threads); DINOSEG_ATTN_SMW overrides for A/B measurements
-int attn_smw() {
-  static const int v = [] {
-    const char* e = getenv("DINOSEG_ATTN_SMW");
-    return (e && atoi(e) == 4) ? 4 : 8;
-  }();
-  return v;
-}
-
-template <int SMW>
-cudaError_t launch_attention_t(const CUtensorMap& qkv, const AttnParams& p, int num_sms, cudaStream_t s) {
-  auto kern = attn_fwd_kernel<kAttnStages, SMW>;
+cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
+  p.timing = g_attn_timing;
+  p.hb = g_heartbeat;
+  attn_plan_items(p);
+  auto kern = attn_fwd_kernel<kAttnStages>;
   constexpr size_t smem = attn_smem_bytes<kAttnStages>();
   static bool attr[64] = {};
   int dev = 0;
@@ -309,15 +301,8 @@ cudaError_t launch_attention_t(const CUtensorMap& qkv, const AttnParams& p, int 
     attr[dev & 63] = true;
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
-  kern<<<grid, att_threads(SMW), smem, s>>>(qkv, p);
+  kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
   return cudaGetLastError();
-}
-
-cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
-  p.timing = g_attn_timing;
-  p.hb = g_heartbeat;
-  attn_plan_items(p);
-  return attn_smw() == 8 ? launch_attention_t<8>(qkv, p, num_sms, s) : launch_attention_t<4>(qkv, p, num_sms, s);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int M, int D, float eps,
