@@ -26,6 +26,7 @@
 
 #include "attention.cuh"
 #include "gemm.cuh"
+#include "head.cuh"
 #include "kernels.cuh"
 #include "mlp.cuh"
 
@@ -506,6 +507,12 @@ struct dinoseg {
   __nv_bfloat16* h2_w = nullptr;    // bf16x3 [H2, 3*256] = [hi | hi | lo], K zero padded 200 -> 256
   float *h1_b = nullptr, *b2 = nullptr, *w3 = nullptr, *b3 = nullptr;
   CUtensorMap tm_h1, tm_h2;
+  // fused head (head.cuh): layer_1 as loaded (fp32), and with the final LayerNorm folded in: [H1, 2D] = [hi | lo], bias
+  float* h1_w32 = nullptr;
+  __nv_bfloat16* h1f_w = nullptr;
+  float* h1f_b = nullptr;
+  CUtensorMap tm_h1f_hi, tm_h1f_lo, tm_w2_hi, tm_w2_lo;
+  bool fused_head = false;          // MLP head on D = 384: LayerNorm -> layer_1/2/3 -> argmax -> replication in ONE kernel
   std::map<std::string, WeightSlot> slots;
   std::set<std::string> have;
   std::vector<void*> allocs;
@@ -656,10 +663,10 @@ int bind_workspace(dinoseg* h, WorkBufs& w, void* ws, size_t ws_bytes, int batch
 
 namespace {
 enum Kind { K_IM2COL = 0, K_CLS, K_GEMM_PATCH, K_LN, K_GEMM_QKV, K_ATTN, K_GEMM_PROJ, K_GEMM_FC1, K_GEMM_FC2,
-            K_GEMM_HEAD, K_HEAD_TAIL, K_REPLICATE, K_MLP_FUSED, K_COUNT };
+            K_GEMM_HEAD, K_HEAD_TAIL, K_REPLICATE, K_MLP_FUSED, K_HEAD_FUSED, K_COUNT };
 const char* const kKindNames[K_COUNT] = {"im2col", "cls_row", "gemm_patch", "layernorm", "gemm_qkv", "attention",
                                          "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_head", "head_tail", "replicate",
-                                         "mlp_fused"};
+                                         "mlp_fused", "head_fused"};
 
 // RAII pair of events around one launch (no-op unless profiling is on)
 struct LaunchScope {
@@ -720,6 +727,9 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   h->device = device;
   h->fused_mlp = cfg->embed_dim == MLP_D && cfg->mlp_hidden == MLP_HID;
   h->mlp_pair = h->fused_mlp;
+  h->fused_head = cfg->head_kind == 0 && cfg->embed_dim == HEAD_D && cfg->head_h1 <= HEAD_N1 && cfg->head_h2 <= HEAD_W3_PITCH - 4 &&
+                  kHeadPart == HEAD_K2;
+  if (const char* mode = getenv("DINOSEG_FUSED_HEAD")) h->fused_head = h->fused_head && atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_PAIR")) {   // CTA-pair kernels: 0.486 vs 0.494 ms (MLP), 0.188 vs 0.212 ms (qkv)
     h->gemm_pair = atoi(mode) != 0;
     h->mlp_pair = h->fused_mlp && atoi(mode) != 0;
@@ -748,6 +758,9 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   rc |= dev_alloc(h, &h->h1_w, size_t(H1) * 3 * D);
   rc |= dev_alloc(h, &h->h2_w, size_t(H2) * 3 * kHeadPart);
   rc |= dev_alloc(h, &h->h1_b, H1);
+  rc |= dev_alloc(h, &h->h1_w32, size_t(H1) * D);
+  rc |= dev_alloc(h, &h->h1f_w, size_t(H1) * 2 * D);
+  rc |= dev_alloc(h, &h->h1f_b, H1);
   rc |= dev_alloc(h, &h->b2, H2);
   rc |= dev_alloc(h, &h->w3, size_t(C) * H2);
   rc |= dev_alloc(h, &h->b3, C);
@@ -802,6 +815,11 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     ok &= make_tmap_2d(&h->tm_pe_p, h->pe_w, D, IM2COL_K3, IM2COL_K3, GEMM_BN / 2);
     ok &= make_tmap_2d(&h->tm_h1, h->h1_w, H1, 3 * D, 3 * D, GEMM_BN);
     ok &= make_tmap_2d(&h->tm_h2, h->h2_w, H2, 3 * kHeadPart, 3 * kHeadPart, GEMM_BN);
+    // fused head: layer_1 [hi | lo] halves as [208 x 64] boxes; layer_2's hi / lo parts of the [hi | hi | lo] packing
+    ok &= make_tmap_2d(&h->tm_h1f_hi, h->h1f_w, H1, D, 2 * D, HEAD_N1);
+    ok &= make_tmap_2d(&h->tm_h1f_lo, h->h1f_w + D, H1, D, 2 * D, HEAD_N1);
+    ok &= make_tmap_2d(&h->tm_w2_hi, h->h2_w, H2, kHeadPart, 3 * kHeadPart, HEAD_N2);
+    ok &= make_tmap_2d(&h->tm_w2_lo, h->h2_w + 2 * kHeadPart, H2, kHeadPart, 3 * kHeadPart, HEAD_N2);
     if (!ok) { h->err = "cuTensorMapEncodeTiled failed for patch/head weights"; rc = -1; }
   }
   if (rc != 0) {
@@ -872,6 +890,8 @@ int dinoseg_set_weight(dinoseg_t* h, const char* key, const float* dev_ptr, cons
   } else {
     DSG_CUDA(h, cudaMemcpyAsync(sl.dst, dev_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
+  if (std::string(key) == "clf.layer_1.weight")     // the fused head folds the final LayerNorm into it (finalize_weights)
+    DSG_CUDA(h, cudaMemcpyAsync(h->h1_w32, dev_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   h->have.insert(key);
   h->weights_dirty = true;          // derived operands (fc1 with or without the folded LayerNorm2) are rebuilt lazily
   return 0;
@@ -1007,10 +1027,42 @@ static int finalize_weights(dinoseg_t* h, cudaStream_t s) {
     }
     DSG_CUDA(h, cudaGetLastError());
   }
+  if (h->cfg.head_kind == 0 && h->cfg.embed_dim == HEAD_D) {   // fused head: final LayerNorm folded into layer_1, hi | lo
+    const int H1 = h->cfg.head_h1;
+    fold_split_ln_weight_kernel<<<(H1 * 32 + 255) / 256, 256, 0, s>>>(h->h1_w32, h->h1_b, h->norm_g, h->norm_b, h->h1f_w,
+                                                                      h->h1f_b, H1, D);
+    DSG_CUDA(h, cudaGetLastError());
+  }
   DSG_CUDA(h, cudaStreamSynchronize(s));
   h->weights_dirty = false;
   h->folded = fold;
   return 0;
+}
+
+cudaError_t launch_head_fused(dinoseg_t* h, const float* x, int M, float* logprobs, uint8_t* lowres, long long* labels,
+                              cudaStream_t s) {
+  static bool attr[64][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int big = h->cfg.n_classes > 8 ? 1 : 0;
+  if (!attr[dev & 63][big]) {
+    cudaError_t e = big ? cudaFuncSetAttribute(head_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(HEAD_SMEM))
+                        : cudaFuncSetAttribute(head_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(HEAD_SMEM));
+    if (e != cudaSuccess) return e;
+    attr[dev & 63][big] = true;
+  }
+  HeadParams p{};
+  p.M = M; p.x = x; p.ln_eps = h->cfg.ln_eps;
+  p.b1f = h->h1f_b; p.b2 = h->b2; p.w3 = h->w3; p.b3 = h->b3;
+  p.H1 = h->cfg.head_h1; p.H2 = h->cfg.head_h2; p.C = h->cfg.n_classes;
+  p.Ntok = h->Ntok; p.g = h->g; p.p = h->p_rep;
+  p.logprobs = logprobs; p.lowres = lowres; p.labels = labels;
+  p.hb = g_heartbeat;
+  const int m_blocks = (M + HEAD_BM - 1) / HEAD_BM;
+  const int grid = m_blocks < h->num_sms ? m_blocks : h->num_sms;
+  if (big) head_fused_kernel<16><<<grid, HEAD_THREADS, HEAD_SMEM, s>>>(h->tm_h1f_hi, h->tm_h1f_lo, h->tm_w2_hi, h->tm_w2_lo, p);
+  else head_fused_kernel<8><<<grid, HEAD_THREADS, HEAD_SMEM, s>>>(h->tm_h1f_hi, h->tm_h1f_lo, h->tm_w2_hi, h->tm_w2_lo, p);
+  return cudaGetLastError();
 }
 
 // Launch sequence of one forward pass over `batch` frames on the buffers of `w` (already bound).
@@ -1155,8 +1207,15 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
   // ---- final norm + head (vision_transformer.py:243, pl_torch_modules.py:243-255) ----
   // The head runs in "bf16x3" precision (operands split into hi + lo bf16 parts, three-fold K): its plain
   // bf16 rounding would otherwise be the largest contribution to the log-prob error.
-  { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, h->norm_g, h->norm_b, w.qkv, M, D, eps, true, s)); ++n; }
   uint8_t* lr = lowres ? lowres : w.lowres;
+  if (h->fused_head) {
+    // ONE kernel: LayerNorm -> layer_1 -> layer_2 -> layer_3 -> log_softmax -> argmax -> p x p replication (head.cuh)
+    LaunchScope ls(h, K_HEAD_FUSED, s);
+    DSG_CUDA(h, launch_head_fused(h, w.x, M, logprobs, lr, (labels && h->p_rep > 0) ? reinterpret_cast<long long*>(labels) : nullptr, s));
+    h->launches = ++n;
+    return 0;
+  }
+  { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, h->norm_g, h->norm_b, w.qkv, M, D, eps, true, s)); ++n; }
   // tail kernel: eight lanes per patch, 32 patches per 256-thread block; it also writes the p x p blocks of the int64
   // label map (reference pl_torch_modules.py:297-298) when the caller wants one and the map is not empty (p = 480 // g)
   const int tail_grid = std::min((batch * h->P + 31) / 32, 16 * h->num_sms);
@@ -1716,6 +1775,14 @@ int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
   h->fused_mlp = on != 0;
   h->mlp_pair = on == 2;
   h->weights_dirty = true;          // fc1 with / without the folded LayerNorm2
+  return 0;
+}
+
+int dinoseg_set_fused_head(dinoseg_t* h, int on) {
+  if (!h) return -1;
+  if (on && !(h->cfg.head_kind == 0 && h->cfg.embed_dim == HEAD_D && h->cfg.head_h1 <= HEAD_N1 && h->cfg.head_h2 <= HEAD_W3_PITCH - 4))
+    DSG_FAIL(h, "the fused head kernel needs the 'mlp' head on embed_dim 384 with head widths <= 208 / 100");
+  h->fused_head = on != 0;
   return 0;
 }
 

@@ -285,6 +285,27 @@ fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ b, 
   if (lane == 0) bf[warp] = b[warp] + acc;
 }
 
+// The same for a bf16x3 consumer: Wf = W * gamma split into hi + lo, stored as [N, 2K] = [hi | lo] (head.cuh).
+__global__ void __launch_bounds__(256)
+fold_split_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ Wf, float* __restrict__ bf, int N, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* w = W + size_t(warp) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float v = w[k];
+    const float f = v * gamma[k];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+    Wf[size_t(warp) * 2 * K + k] = hi;
+    Wf[size_t(warp) * 2 * K + K + k] = __float2bfloat16_rn(f - __bfloat162float(hi));
+    acc = fmaf(v, beta[k], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) bf[warp] = b[warp] + acc;
+}
+
 // D = 384, plain bf16 output: four rows per warp (eight lanes per row), 32 rows per 256-thread block
 __global__ void __launch_bounds__(256)
 layernorm384_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,

@@ -217,6 +217,9 @@ int dinoseg_op_mlp_ln(float* x, float eps, const void* W1f_bf16, const float* b1
 /* 0: unfused LN / fc1 / fc2 kernels; 1: fused MLP kernel, one CTA per row block; 2: fused MLP kernel run by CTA pairs
  * (cta_group::2); 2 is the default where the fused kernel applies (embed_dim 384, mlp_hidden 1536) */
 int dinoseg_set_fused_mlp(dinoseg_t* h, int on);
+/* 1 (default where it applies: 'mlp' head, embed_dim 384): final LayerNorm -> layer_1 -> layer_2 -> layer_3 -> log_softmax
+ * -> argmax -> p x p replication in ONE kernel (csrc/head.cuh); 0: the separate LayerNorm / GEMM / GEMM / tail kernels */
+int dinoseg_set_fused_head(dinoseg_t* h, int on);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
                          float eps, void* stream);
 int dinoseg_op_posembed(const float* pos_src, float* out, int G0, int g, int D, void* stream);

@@ -438,6 +438,47 @@ def test_fused_mlp_matches_unfused_path():
     assert (b.cpu() - ref).abs().max().item() <= TOL_REL_TRAINED * rng
 
 
+@pytest.mark.parametrize("variant,res,batch", [("reference_init", 240, 3), ("trained_like", 224, 2), ("trained_like", 64, 5),
+                                               ("reference_init", 480, 9)])
+def test_fused_head_matches_the_kernel_chain(variant, res, batch):
+    """The one-kernel head (final LayerNorm -> layer_1 -> layer_2 -> layer_3 -> log_softmax -> argmax -> replication,
+    csrc/head.cuh; reference vision_transformer.py:243, pl_torch_modules.py:117-124, :294-298) against the separate
+    LayerNorm / GEMM / GEMM / tail kernels it replaces: both evaluate the head in bf16x3, so their log-probs agree far
+    inside the bf16-vs-fp32 tolerance; label maps are the replication of each path's own argmax."""
+    lib = _lib.load()
+    m, cfg, sd = _model("vit_small", 2, 21, variant)
+    x = synthetic.make_frames(batch, res, seed=res).cuda()
+    g = res // 8
+    p = 480 // g
+    lp1, low1, lab1 = m.infer(x, want_logprobs=True, want_lowres=True, want_labels=True)
+    n_fused = m.last_launch_count()
+    assert lib.dinoseg_set_fused_head(m._handle, 0) == 0
+    try:
+        lp0, low0, lab0 = m.infer(x, want_logprobs=True, want_lowres=True, want_labels=True)
+        n_chain = m.last_launch_count()
+    finally:
+        assert lib.dinoseg_set_fused_head(m._handle, 1) == 0
+    torch.cuda.synchronize()
+    assert n_chain == n_fused + 3                                  # LayerNorm + 2 GEMMs + tail -> 1 kernel
+    rng = float(lp0.max() - lp0.min())
+    d = float((lp1 - lp0).abs().max())
+    _record(case=f"fused_head_{variant}_{res}", max_abs_vs_chain=d, range=rng)
+    assert d <= 2e-4 * max(1.0, rng), (d, rng)
+    assert torch.isfinite(lp1).all() and (torch.logsumexp(lp1.double(), dim=1).abs() <= 1e-5).all()
+    assert torch.equal(low1.reshape(-1).long(), lp1.argmax(1))
+    assert torch.equal(lab1, low1.long().repeat_interleave(p, dim=1).repeat_interleave(p, dim=2))
+    differ = low1 != low0
+    if differ.any():                                               # only where the chain's top-2 margin is below the difference
+        srt = torch.sort(lp0, dim=1).values
+        margin = (srt[:, -1] - srt[:, -2]).reshape(low0.shape)
+        assert (margin[differ] <= 2 * d + 1e-7).all()
+    # only one of the outputs requested
+    _, low_only, _ = m.infer(x, want_logprobs=False, want_lowres=True)
+    _, _, lab_only = m.infer(x, want_logprobs=False, want_labels=True)
+    torch.cuda.synchronize()
+    assert torch.equal(low_only, low1) and torch.equal(lab_only, lab1)
+
+
 def test_weight_update_is_picked_up():
     """load_state_dict after the first forward re-packs the bf16 weights (no stale cache)."""
     m, cfg, sd = _model("vit_small", 1, 1, "reference_init")
