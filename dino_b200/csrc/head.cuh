@@ -213,7 +213,16 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
     uint32_t u = 0;
     for (int bi = 0; bi < my_blocks; ++bi) {
       const int r0 = block_row0(bi);
-      // statistics of this block's rows (the first read of x: HBM -> L2); overlaps the tensor-pipe work of block bi-1
+      // the NEXT block's rows -> L2 now (192 KB: 12 lines per thread), so that its statistics pass finds them there
+      if (bi + 1 < my_blocks) {
+        const int rn = block_row0(bi + 1);
+        const char* base = reinterpret_cast<const char*>(p.x + size_t(rn) * HEAD_D);
+        const size_t bytes = size_t(max(0, min(HEAD_BM, p.M - rn))) * HEAD_D * sizeof(float);
+        for (size_t off = size_t(threadIdx.x - 64) * 128; off < bytes; off += 128 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      }
+      // statistics of this block's rows (first read of x; L2 hits except for the first block); overlaps the tensor-pipe
+      // work of block bi-1
       for (int pass = 0; pass < 8; ++pass) {
         const int r = lw * 32 + pass * 4 + grp;
         const int row = r0 + r;
@@ -227,24 +236,32 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
       }
       __syncwarp();                               // statistics are written and read by the lanes of one warp
       for (int kb = 0; kb < HEAD_KB1; ++kb, ++u) {
+        // columns kb*64 + sub*4 + {0, 32}: float4 numbers kb*16 + sub + {0, 8} of the row (second read of x: L2).  All 16
+        // loads of the warp's 32 rows are issued before the first wait: the latency is paid once per k-block.
+        float4 v0[8], v1[8];
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int row = r0 + lw * 32 + pass * 4 + grp;
+          const bool live = row < p.M;
+          const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(live ? row : 0) * HEAD_D) + kb * 16 + sub;
+          v0[pass] = live ? __ldg(xr) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[pass] = live ? __ldg(xr + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (u >= 2) mbar_wait(&empty[u & 1], ((u >> 1) - 1) & 1);
         if (kb < 2 && bi > 0) mbar_wait(mma2_done, (bi - 1) & 1);
         uint8_t* a_hi = stage1(u);
         uint8_t* a_lo = a_hi + HEAD_A_TILE;
-        // columns kb*64 + sub*4 + {0, 32}: float4 numbers kb*16 + sub + {0, 8} of the row (second read of x: L2)
-#pragma unroll 2
+#pragma unroll
         for (int pass = 0; pass < 8; ++pass) {
           const int r = lw * 32 + pass * 4 + grp;
-          const int row = r0 + r;
-          const bool live = row < p.M;
-          const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(live ? row : 0) * HEAD_D) + kb * 16 + sub;
-          const float4 v0 = live ? __ldg(xr) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 v1 = live ? __ldg(xr + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool live = r0 + r < p.M;
           const float2 st = sStats[r];
           const float mean = live ? st.x : 0.f, rstd = live ? st.y : 0.f;
           uint4 hi, lo;
-          split_pack8(make_float4((v0.x - mean) * rstd, (v0.y - mean) * rstd, (v0.z - mean) * rstd, (v0.w - mean) * rstd),
-                      make_float4((v1.x - mean) * rstd, (v1.y - mean) * rstd, (v1.z - mean) * rstd, (v1.w - mean) * rstd), hi, lo);
+          split_pack8(make_float4((v0[pass].x - mean) * rstd, (v0[pass].y - mean) * rstd, (v0[pass].z - mean) * rstd,
+                                  (v0[pass].w - mean) * rstd),
+                      make_float4((v1[pass].x - mean) * rstd, (v1[pass].y - mean) * rstd, (v1[pass].z - mean) * rstd,
+                                  (v1[pass].w - mean) * rstd), hi, lo);
           // v0 -> 8-byte half sub&1 of 16-byte chunk sub/2; v1 -> the same half of chunk sub/2 + 4
           const uint32_t off0 = uint32_t(r) * 128u + (uint32_t((sub >> 1) ^ (r & 7)) << 4) + uint32_t(sub & 1) * 8u;
           const uint32_t off1 = uint32_t(r) * 128u + (uint32_t(((sub >> 1) + 4) ^ (r & 7)) << 4) + uint32_t(sub & 1) * 8u;
