@@ -16,13 +16,14 @@
 // The LayerNorm's gamma / beta are folded into layer_1 at weight-load time (W1 diag(gamma), b1 + W1 beta), so the
 // kernel only normalises.
 //
-// Warp roles (448 threads, 1 CTA / SM):
+// Warp roles (576 threads, 1 CTA / SM):
 //   warp 0       TMA producer: W1 (hi, lo) k-blocks [208 x 64] into the phase-1 ring, W2 (hi, lo) k-blocks [112 x 64]
 //   warp 1       TMEM allocation + single-thread tcgen05.mma issuer
 //   warps 2..5   LayerNorm: row statistics of the NEXT row block while the current one is in the tensor pipe, then per
 //                k-block (64 columns) the A operand tiles xhat_hi / xhat_lo [128 x 64] bf16 in the UMMA layout
-//   warps 6..9   epilogue 1: acc1 (+ b1, ReLU) -> h1_hi / h1_lo as the A operand of layer 2 in shared memory
-//   warps 10..13 epilogue 2: acc2 (+ b2, ReLU) -> layer_3 -> log_softmax -> argmax -> log-probs / low-res map / labels
+//   warps 6..13  epilogue 1 (two warps per TMEM lane quarter, alternate 32-column chunks): acc1 (+ b1, ReLU) -> h1_hi /
+//                h1_lo as the A operand of layer 2 in shared memory - it sits between the two GEMMs of a row block
+//   warps 14..17 epilogue 2: acc2 (+ b2, ReLU) -> layer_3 -> log_softmax -> argmax -> log-probs / low-res map / labels
 //
 // Shared memory (184 KB + tables): phase 1 uses two stages of [xhat_hi 16 | xhat_lo 16 | W1_hi 26 | W1_lo 26] KB;
 // phase 2 overlays the same bytes with h1 (4 k-blocks x [hi 16 | lo 16] KB) and a two-stage W2 ring (2 x 28 KB): layer 2
@@ -66,7 +67,7 @@ constexpr int HEAD_REGION = HEAD_H1_BYTES + 2 * HEAD_STAGE2;      // 184 KB (>= 
 static_assert(HEAD_REGION >= 2 * HEAD_STAGE1, "phase-2 layout must cover the phase-1 ring");
 constexpr int HEAD_W3_PITCH = 104;
 constexpr int HEAD_TABLE_FLOATS = HEAD_N1 + HEAD_N2 + HEAD_MAX_C * HEAD_W3_PITCH + HEAD_MAX_C;   // b1f, b2, W3, b3
-constexpr int HEAD_THREADS = 64 + 3 * 128;            // 448
+constexpr int HEAD_THREADS = 64 + 128 + 256 + 128;    // 576
 constexpr size_t HEAD_SMEM = size_t(HEAD_REGION) + HEAD_TABLE_FLOATS * sizeof(float) + HEAD_BM * sizeof(float2) + 256 +
                              1024;                    // + statistics + barriers + alignment slack
 
@@ -93,8 +94,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
   uint64_t* w2_empty = bars + 6;      // 2
   uint64_t* mma1_done = bars + 8;     // acc1 complete; the phase-1 ring is dead (h1 / W2 may overlay it)
   uint64_t* mma2_done = bars + 9;     // acc2 complete; h1 / W2 are dead (the next row block's phase 1 may start)
-  uint64_t* h1_ready = bars + 10;     // 4 arrivals: epilogue 1 has written h1
-  uint64_t* acc1_empty = bars + 11;   // 4 arrivals: epilogue 1 has read acc1
+  uint64_t* h1_ready = bars + 10;     // 8 arrivals: epilogue 1 has written h1
+  uint64_t* acc1_empty = bars + 11;   // 8 arrivals: epilogue 1 has read acc1
   uint64_t* acc2_empty = bars + 12;   // 4 arrivals: epilogue 2 has read acc2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
@@ -118,8 +119,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
     }
     mbar_init(mma1_done, 1);
     mbar_init(mma2_done, 1);
-    mbar_init(h1_ready, 4);
-    mbar_init(acc1_empty, 4);
+    mbar_init(h1_ready, 8);
+    mbar_init(acc1_empty, 8);
     mbar_init(acc2_empty, 4);
     fence_mbar_init();
   }
@@ -275,16 +276,17 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
         if (lane == 0) mbar_arrive(&full[u & 1]);
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 14) {
     // ---------------- epilogue 1: acc1 -> relu(acc1 + b1) -> h1_hi / h1_lo (A operand of layer 2) ----------------
     const int row = (warp & 3) * 32 + lane;        // TMEM lane = row of the block
+    const int half = (warp - 6) >> 2;              // this warp takes the 32-column chunks half, half + 2, half + 4, half + 6
     const uint32_t acc = tmem_base + (uint32_t((warp & 3) * 32) << 16) + ACC1_COL;
     for (int bi = 0; bi < my_blocks; ++bi) {
       mbar_wait(mma1_done, bi & 1);
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {                // 32 columns per step: 0..207 hold data, 208..255 are zero padding
+      for (int c = half; c < 8; c += 2) {          // columns 0..207 hold data, 208..255 are zero padding
         float v[32];
         if (c < 6) {
           uint32_t r[32];
@@ -304,7 +306,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (c == 6) {                              // every column of acc1 is in registers: the next block may overwrite it
+        if (c >= 6) {                              // this warp's last chunk: its part of acc1 is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc1_empty);
