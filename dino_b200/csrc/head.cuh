@@ -71,6 +71,14 @@ constexpr int HEAD_THREADS = 64 + 128 + 256 + 128;    // 576
 constexpr size_t HEAD_SMEM = size_t(HEAD_REGION) + HEAD_TABLE_FLOATS * sizeof(float) + HEAD_BM * sizeof(float2) + 256 +
                              1024;                    // + statistics + barriers + alignment slack
 
+// -DDSG_HEAD_TIMING: the MMA issuer of CTA 0 accumulates the cycles it spends waiting per barrier and in total; the
+// totals land in the heartbeat array at [900 + 2*i] (64-bit each), read with dinoseg_debug_heartbeat (tools/head_timing.py)
+#ifdef DSG_HEAD_TIMING
+#define HEAD_T(i) do { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } while (0)
+#else
+#define HEAD_T(i) do { } while (0)
+#endif
+
 template <int MAXC>
 __global__ void __launch_bounds__(HEAD_THREADS, 1)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_constant__ CUtensorMap tmW1lo,
@@ -170,10 +178,18 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
       constexpr uint32_t idesc1 = umma_idesc_bf16(HEAD_BM, HEAD_N1, 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(HEAD_BM, HEAD_N2, 0);
       uint32_t u = 0, v = 0;
+#ifdef DSG_HEAD_TIMING
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tprev = clock64();
+#endif
       for (int bi = 0; bi < my_blocks; ++bi) {
+        HEAD_T(7);
         if (bi > 0) { mbar_wait(acc1_empty, (bi - 1) & 1); tc_fence_after(); }
+        HEAD_T(0);
         for (int kb = 0; kb < HEAD_KB1; ++kb, ++u) {
+          HEAD_T(7);
           mbar_wait(&full[u & 1], (u >> 1) & 1);
+          HEAD_T(kb == 0 ? 1 : 2);
           tc_fence_after();
           const uint32_t st = smem_u32(stage1(u));
           const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + HEAD_A_TILE);
@@ -187,11 +203,16 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
           tc_commit(&empty[u & 1]);
         }
         tc_commit(mma1_done);
+        HEAD_T(7);
         mbar_wait(h1_ready, bi & 1);
+        HEAD_T(3);
         if (bi > 0) mbar_wait(acc2_empty, (bi - 1) & 1);
+        HEAD_T(4);
         tc_fence_after();
         for (int kb = 0; kb < HEAD_KB2; ++kb, ++v) {
+          HEAD_T(7);
           mbar_wait(&w2_full[v & 1], (v >> 1) & 1);
+          HEAD_T(5);
           tc_fence_after();
           const uint32_t st = smem_u32(stage2(v));
           const uint64_t a_hi = umma_desc_sw128(smem_u32(h1_tile(kb, 0))), a_lo = umma_desc_sw128(smem_u32(h1_tile(kb, 1)));
@@ -206,6 +227,13 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
         }
         tc_commit(mma2_done);
       }
+#ifdef DSG_HEAD_TIMING
+      HEAD_T(7);
+      if (p.hb != nullptr && blockIdx.x == 0) {
+        tacc[6] = my_blocks;
+        for (int i = 0; i < 8; ++i) reinterpret_cast<long long*>(p.hb + 900)[i] = tacc[i];
+      }
+#endif
     }
   } else if (warp < 6) {
     // ---------------- LayerNorm warps: statistics, then the A operand k-block by k-block ----------------
