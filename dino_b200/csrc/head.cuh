@@ -19,12 +19,11 @@
 // Warp roles (576 threads, 1 CTA / SM):
 //   warp 0       TMA producer: W1 (hi, lo) k-blocks [208 x 64] into the phase-1 ring, W2 (hi, lo) k-blocks [112 x 64]
 //   warp 1       TMEM allocation + single-thread tcgen05.mma issuer
-//   warps 2..9   LayerNorm: per k-block (64 columns) the A operand tiles xhat_hi / xhat_lo [128 x 64] bf16 in the UMMA
-//                layout, from x (L2, loads one k-block ahead) and the row statistics computed two row blocks earlier
-//   warps 10..17 epilogue 1 (two warps per TMEM lane quarter, alternate 32-column chunks): acc1 (+ b1, ReLU) -> h1_hi /
-//                h1_lo as the A operand of layer 2 in shared memory - it sits between the two GEMMs of a row block;
-//                then the row statistics of the block two ahead (first read of x); then, four of them, epilogue 2:
-//                acc2 (+ b2, ReLU) -> layer_3 -> log_softmax -> argmax -> log-probs / low-res map / labels
+//   warps 2..5   LayerNorm: row statistics of the NEXT row block while the current one is in the tensor pipe, then per
+//                k-block (64 columns) the A operand tiles xhat_hi / xhat_lo [128 x 64] bf16 in the UMMA layout
+//   warps 6..13  epilogue 1 (two warps per TMEM lane quarter, alternate 32-column chunks): acc1 (+ b1, ReLU) -> h1_hi /
+//                h1_lo as the A operand of layer 2 in shared memory - it sits between the two GEMMs of a row block
+//   warps 14..17 epilogue 2: acc2 (+ b2, ReLU) -> layer_3 -> log_softmax -> argmax -> log-probs / low-res map / labels
 //
 // Shared memory (184 KB + tables): phase 1 uses two stages of [xhat_hi 16 | xhat_lo 16 | W1_hi 26 | W1_lo 26] KB;
 // phase 2 overlays the same bytes with h1 (4 k-blocks x [hi 16 | lo 16] KB) and a two-stage W2 ring (2 x 28 KB): layer 2
@@ -68,8 +67,8 @@ constexpr int HEAD_REGION = HEAD_H1_BYTES + 2 * HEAD_STAGE2;      // 184 KB (>= 
 static_assert(HEAD_REGION >= 2 * HEAD_STAGE1, "phase-2 layout must cover the phase-1 ring");
 constexpr int HEAD_W3_PITCH = 104;
 constexpr int HEAD_TABLE_FLOATS = HEAD_N1 + HEAD_N2 + HEAD_MAX_C * HEAD_W3_PITCH + HEAD_MAX_C;   // b1f, b2, W3, b3
-constexpr int HEAD_THREADS = 64 + 256 + 256;          // 576
-constexpr size_t HEAD_SMEM = size_t(HEAD_REGION) + HEAD_TABLE_FLOATS * sizeof(float) + 2 * HEAD_BM * sizeof(float2) + 256 +
+constexpr int HEAD_THREADS = 64 + 128 + 256 + 128;    // 576
+constexpr size_t HEAD_SMEM = size_t(HEAD_REGION) + HEAD_TABLE_FLOATS * sizeof(float) + HEAD_BM * sizeof(float2) + 256 +
                              1024;                    // + statistics + barriers + alignment slack
 
 // -DDSG_HEAD_TIMING: the MMA issuer of CTA 0 accumulates the cycles it spends waiting per barrier and in total; the
@@ -95,9 +94,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
   float* sB2 = sB1 + HEAD_N1;                                    // [112]
   float* sW3 = sB2 + HEAD_N2;                                    // [HEAD_MAX_C][104]
   float* sB3 = sW3 + HEAD_MAX_C * HEAD_W3_PITCH;                 // [HEAD_MAX_C]
-  float2* sStats = reinterpret_cast<float2*>(sB3 + HEAD_MAX_C);  // [2][128] (mean, rstd) per row, row blocks bi and bi+1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStats + 2 * HEAD_BM);
-  uint64_t* full = bars;              // 2: stage filled (8 LayerNorm warps + producer's expect_tx / TMA bytes)
+  float2* sStats = reinterpret_cast<float2*>(sB3 + HEAD_MAX_C);  // [128] (mean, rstd) of the row block being filled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStats + HEAD_BM);
+  uint64_t* full = bars;              // 2: stage filled (4 LayerNorm warps + producer's expect_tx / TMA bytes)
   uint64_t* empty = bars + 2;         // 2: the MMAs reading the stage have retired
   uint64_t* w2_full = bars + 4;       // 2
   uint64_t* w2_empty = bars + 6;      // 2
@@ -106,8 +105,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
   uint64_t* h1_ready = bars + 10;     // 8 arrivals: epilogue 1 has written h1
   uint64_t* acc1_empty = bars + 11;   // 8 arrivals: epilogue 1 has read acc1
   uint64_t* acc2_empty = bars + 12;   // 4 arrivals: epilogue 2 has read acc2
-  uint64_t* stats_ready = bars + 13;  // 2 (one per sStats buffer), 8 arrivals: the statistics of a row block are written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -122,7 +120,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmW1hi); tma_prefetch_desc(&tmW1lo); tma_prefetch_desc(&tmW2hi); tma_prefetch_desc(&tmW2lo);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full[s], 9);
+      mbar_init(&full[s], 5);
       mbar_init(&empty[s], 1);
       mbar_init(&w2_full[s], 1);
       mbar_init(&w2_empty[s], 1);
@@ -132,8 +130,6 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
     mbar_init(h1_ready, 8);
     mbar_init(acc1_empty, 8);
     mbar_init(acc2_empty, 4);
-    mbar_init(&stats_ready[0], 8);
-    mbar_init(&stats_ready[1], 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -239,54 +235,56 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
       }
 #endif
     }
-  } else if (warp < 10) {
-    // ---------------- LayerNorm warps (8): the A operand, k-block by k-block ----------------
-    // Eight lanes per row, four rows per pass; warp w takes rows w*16 .. w*16+15 of the row block (four passes).  For
-    // k-block kb a lane reads the float4 numbers kb*16 + sub + {0, 8} of its rows (second read of x: L2), normalises with
-    // the row's statistics, splits into bf16 hi + lo and writes both tiles.  The loads run ONE K-BLOCK AHEAD of the
-    // arithmetic (across row blocks too: x is read-only), so their latency hides behind the previous k-block's work.
+  } else if (warp < 6) {
+    // ---------------- LayerNorm warps: statistics, then the A operand k-block by k-block ----------------
+    // Eight lanes per row, four rows per pass (ln384_stats).  Warp w takes rows w*32 .. w*32+31 of the row block.
     const int lw = warp - 2, sub = lane & 7, grp = lane >> 3;
-    const int total = my_blocks * HEAD_KB1;
-    float4 v0[4], v1[4], n0[4], n1[4];
-    auto load_kb = [&](int q, float4 (&a0)[4], float4 (&a1)[4]) {   // q: k-block number over all of this CTA's row blocks
-      const int bq = q / HEAD_KB1, kq = q - bq * HEAD_KB1;
-      const int r0q = block_row0(bq);
-#pragma unroll
-      for (int pass = 0; pass < 4; ++pass) {
-        const int row = r0q + lw * 16 + pass * 4 + grp;
-        const bool live = row < p.M;
-        const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(live ? row : 0) * HEAD_D) + kq * 16 + sub;
-        a0[pass] = live ? __ldg(xr) : make_float4(0.f, 0.f, 0.f, 0.f);
-        a1[pass] = live ? __ldg(xr + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    if (total > 0) load_kb(0, v0, v1);
     uint32_t u = 0;
     for (int bi = 0; bi < my_blocks; ++bi) {
       const int r0 = block_row0(bi);
-      // rows of the block three ahead -> L2 now (192 KB: 6 lines per thread): its statistics pass runs two blocks ahead
-      for (int ahead = (bi == 0 ? 0 : 3); ahead <= 3 && bi + ahead < my_blocks; ++ahead) {
-        const int rn = block_row0(bi + ahead);
+      // the NEXT block's rows -> L2 now (192 KB: 12 lines per thread), so that its statistics pass finds them there
+      if (bi + 1 < my_blocks) {
+        const int rn = block_row0(bi + 1);
         const char* base = reinterpret_cast<const char*>(p.x + size_t(rn) * HEAD_D);
         const size_t bytes = size_t(max(0, min(HEAD_BM, p.M - rn))) * HEAD_D * sizeof(float);
-        for (size_t off = size_t(threadIdx.x - 64) * 128; off < bytes; off += 256 * 128)
+        for (size_t off = size_t(threadIdx.x - 64) * 128; off < bytes; off += 128 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
       }
-      mbar_wait(&stats_ready[bi & 1], (bi >> 1) & 1);   // written by the epilogue warps, two row blocks ahead
-      // (one barrier per buffer: the writers run two blocks ahead, a single barrier could advance two phases)
-      const float2* stats = sStats + (bi & 1) * HEAD_BM;
+      // statistics of this block's rows (first read of x; L2 hits except for the first block); overlaps the tensor-pipe
+      // work of block bi-1
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = lw * 32 + pass * 4 + grp;
+        const int row = r0 + r;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(row < p.M ? row : 0) * HEAD_D);
+        float4 v[LN384_V];
+#pragma unroll
+        for (int i = 0; i < LN384_V; ++i) v[i] = row < p.M ? __ldg(xr + i * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float mean, rstd;
+        ln384_stats(v, p.ln_eps, mean, rstd);
+        if (sub == 0) sStats[r] = make_float2(mean, rstd);
+      }
+      __syncwarp();                               // statistics are written and read by the lanes of one warp
       for (int kb = 0; kb < HEAD_KB1; ++kb, ++u) {
-        const int q = bi * HEAD_KB1 + kb;
-        if (q + 1 < total) load_kb(q + 1, n0, n1);
+        // columns kb*64 + sub*4 + {0, 32}: float4 numbers kb*16 + sub + {0, 8} of the row (second read of x: L2).  All 16
+        // loads of the warp's 32 rows are issued before the first wait: the latency is paid once per k-block.
+        float4 v0[8], v1[8];
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int row = r0 + lw * 32 + pass * 4 + grp;
+          const bool live = row < p.M;
+          const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(live ? row : 0) * HEAD_D) + kb * 16 + sub;
+          v0[pass] = live ? __ldg(xr) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[pass] = live ? __ldg(xr + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (u >= 2) mbar_wait(&empty[u & 1], ((u >> 1) - 1) & 1);
         if (kb < 2 && bi > 0) mbar_wait(mma2_done, (bi - 1) & 1);
         uint8_t* a_hi = stage1(u);
         uint8_t* a_lo = a_hi + HEAD_A_TILE;
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          const int r = lw * 16 + pass * 4 + grp;
+        for (int pass = 0; pass < 8; ++pass) {
+          const int r = lw * 32 + pass * 4 + grp;
           const bool live = r0 + r < p.M;
-          const float2 st = stats[r];
+          const float2 st = sStats[r];
           const float mean = live ? st.x : 0.f, rstd = live ? st.y : 0.f;
           uint4 hi, lo;
           split_pack8(make_float4((v0[pass].x - mean) * rstd, (v0[pass].y - mean) * rstd, (v0[pass].z - mean) * rstd,
@@ -304,43 +302,14 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[u & 1]);
-#pragma unroll
-        for (int pass = 0; pass < 4; ++pass) { v0[pass] = n0[pass]; v1[pass] = n1[pass]; }
       }
     }
-  } else {
-    // ---------------- epilogue warps (8): epilogue 1, row statistics two blocks ahead, epilogue 2 ----------------
+  } else if (warp < 14) {
+    // ---------------- epilogue 1: acc1 -> relu(acc1 + b1) -> h1_hi / h1_lo (A operand of layer 2) ----------------
     const int row = (warp & 3) * 32 + lane;        // TMEM lane = row of the block
-    const int half = (warp - 10) >> 2;             // epilogue 1: this warp takes the 32-column chunks half, half + 2, ...
+    const int half = (warp - 6) >> 2;              // this warp takes the 32-column chunks half, half + 2, half + 4, half + 6
     const uint32_t acc = tmem_base + (uint32_t((warp & 3) * 32) << 16) + ACC1_COL;
-    const uint32_t acc2 = tmem_base + (uint32_t((warp & 3) * 32) << 16) + ACC2_COL;
-    const int P = p.g * p.g, W = p.g * p.p;
-    // LayerNorm statistics, TWO row blocks ahead of the tensor pipe (first read of x: HBM / L2 -> registers; the fill
-    // re-reads it from L2): warp w takes rows w*16 .. w*16+15, four rows per pass, eight lanes per row (ln384_stats).
-    // sStats is double buffered: the statistics of block bi+2 overwrite those of block bi after its last fill (which
-    // precedes mma1_done(bi)).
-    const int sw = warp - 10, sub = lane & 7, grp = lane >> 3;
-    auto stats_block = [&](int bi) {
-      const int r0 = block_row0(bi);
-      float2* st = sStats + (bi & 1) * HEAD_BM;
-      for (int pass = 0; pass < 4; ++pass) {
-        const int r = sw * 16 + pass * 4 + grp;
-        const int rowg = r0 + r;
-        const float4* xr = reinterpret_cast<const float4*>(p.x + size_t(rowg < p.M ? rowg : 0) * HEAD_D);
-        float4 v[LN384_V];
-#pragma unroll
-        for (int i = 0; i < LN384_V; ++i) v[i] = rowg < p.M ? __ldg(xr + i * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float mean, rstd;
-        ln384_stats(v, p.ln_eps, mean, rstd);
-        if (sub == 0) st[r] = make_float2(mean, rstd);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&stats_ready[bi & 1]);
-    };
-    if (my_blocks > 0) stats_block(0);
-    if (my_blocks > 1) stats_block(1);
     for (int bi = 0; bi < my_blocks; ++bi) {
-      // ---- epilogue 1: acc1 -> relu(acc1 + b1) -> h1_hi / h1_lo (A operand of layer 2); it sits between the two GEMMs ----
       mbar_wait(mma1_done, bi & 1);
       __syncwarp();
       tc_fence_after();
@@ -385,9 +354,13 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(h1_ready);
-      if (bi + 2 < my_blocks) stats_block(bi + 2);
-      if (half != 0) continue;                     // epilogue 2 is one thread per row: four of the eight warps
-      // ---- epilogue 2: acc2 -> relu(acc2 + b2) -> layer_3 -> log_softmax -> argmax -> outputs ----
+    }
+  } else {
+    // ---------------- epilogue 2: acc2 -> relu(acc2 + b2) -> layer_3 -> log_softmax -> argmax -> outputs ----------------
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t acc = tmem_base + (uint32_t((warp & 3) * 32) << 16) + ACC2_COL;
+    const int P = p.g * p.g, W = p.g * p.p;
+    for (int bi = 0; bi < my_blocks; ++bi) {
       mbar_wait(mma2_done, bi & 1);
       __syncwarp();                                // (rows that skip the output part below rejoin here)
       tc_fence_after();
@@ -397,7 +370,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmW1hi, const __grid_const
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {                // columns >= H2 carry relu(0 + 0) = 0 and W3 is zero padded there
         uint32_t r[32];
-        tmem_ld_x32(acc2 + uint32_t(c * 32), r);
+        tmem_ld_x32(acc + uint32_t(c * 32), r);
         tmem_ld_wait();
         if (c == 3) {
           tc_fence_before();
