@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +23,7 @@
 #include <emmintrin.h>
 #include <set>
 #include <string>
+#include <system_error>
 #include <vector>
 
 #include "attention.cuh"
@@ -1720,6 +1722,25 @@ int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* 
                         : epi == EPI_GELU_BF16 ? launch_gemm_pair<EPI_GELU_BF16>(ta, tw, to, to, p, sms, s)
                                                : launch_gemm_pair<EPI_RESID_F32>(ta, tw, to, to, p, sms, s);
   return e == cudaSuccess ? 0 : -3;
+}
+
+// Test hook for the worker pool of the host entry points: create a pool of n threads where the creation of thread number
+// fail_at throws (fail_at < 0: none does), run one task per requested thread, destroy the pool.  Returns the number of
+// threads the pool ended up with (0 when not even the first could be created: the caller's DMA fallback), or -1 if the
+// tasks did not all run.  A partial failure must neither terminate the process nor leak a worker.
+int dinoseg_debug_host_pool(int n, int fail_at) {
+  if (n < 1 || n > 64) return -1;
+  int size = 0;
+  std::atomic<int> ran{0};
+  try {
+    HostPool pool(n, [fail_at](int i) { if (i == fail_at) throw std::system_error(std::make_error_code(std::errc::resource_unavailable_try_again)); });
+    size = pool.size();
+    for (int i = 0; i < n; ++i) pool.submit([&ran] { ran.fetch_add(1); });
+    pool.wait_all();
+  } catch (...) {
+    return 0;
+  }
+  return ran.load() == n ? size : -1;
 }
 
 int dinoseg_debug_attn_items(int B, int H, int N, int32_t* items, int max_items) {

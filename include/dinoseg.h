@@ -191,6 +191,9 @@ int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* 
                          float col_scale, int scale_cols, void* stream);
 /* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16 (q pre-scaled) */
 int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int H, void* stream);
+/* Test hook (pure CPU): worker pool of the host entry points with n threads where the creation of thread fail_at fails
+ * (< 0: none); returns the threads the pool ended up with (0: none, the caller falls back to the DMA path), -1 on error. */
+int dinoseg_debug_host_pool(int n, int fail_at);
 /* Host-side copy of the attention kernel's work-item plan (pure CPU): item i -> {bh0, q0_0, bh1, q0_1, active1, dual}
  * (frame*H + head and first query row of warpgroup 0 / 1).  items == NULL returns the item count. */
 int dinoseg_debug_attn_items(int B, int H, int N, int32_t* items, int max_items);

@@ -386,6 +386,17 @@ def test_folder_inference_host_logic(tmp_path):
     assert folder.label_colormap()[:4].tolist() == [[0, 0, 0], [128, 0, 0], [0, 128, 0], [128, 128, 0]]
 
 
+def test_host_worker_pool_survives_a_failing_thread_creation():
+    """std::thread creation can fail (EAGAIN: pids / nproc limit).  A partial failure keeps the smaller pool - it must not
+    unwind with joinable threads (std::terminate) - and a failure of the very first thread is reported to the caller, who
+    falls back to the DMA path (dinoseg_api.cu: HostPool, predict_host_submit_impl)."""
+    lib = _lib.load()
+    assert lib.dinoseg_debug_host_pool(6, -1) == 6          # all threads, all tasks ran
+    assert lib.dinoseg_debug_host_pool(6, 3) == 3           # threads 0..2 exist and do all the work
+    assert lib.dinoseg_debug_host_pool(6, 1) == 1
+    assert lib.dinoseg_debug_host_pool(6, 0) == 0           # no thread at all: the caller's fallback
+
+
 def test_product_code_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under dino_b200/ or dt_segmentation/ may use it."""
     for pkg in ("dino_b200", "dt_segmentation"):
