@@ -8,8 +8,8 @@
 //
 // q/k/v are read straight out of the qkv GEMM output [B, N, 3*D] bf16 (column = which*D + h*64 + d,
 // exactly nn.Linear's output order, reference :82) through ONE 3-D tensor map {3D, N, B}; rows >= N
-// of a frame are zero-filled by TMA.  q is pre-scaled by dh^-0.5 (exact in bf16: 0.125) by the qkv
-// GEMM epilogue.
+// of a frame are zero-filled by TMA.  q is pre-scaled by dh^-0.5 * log2(e) by the qkv GEMM epilogue (in fp32,
+// before its one rounding to bf16), so S comes out of the tensor pipe in log2 units: P = 2^S.
 //
 // Work decomposition: a work item is a pair of 128-query tiles (256 queries) of one (b,h).  The
 // kernel is persistent (grid = #SMs, item = blockIdx.x + k*gridDim.x) and streams the 128-key K/V
@@ -35,8 +35,10 @@
 // flop per clock; 2*128*128 exps per key tile = 2048 MUFU clocks vs 1354 clocks of MMA):
 //   * a quarter of the exponentials is evaluated with a degree-3 polynomial on the FMA/ALU pipes
 //     (exp2_poly_x2, packed fp32x2 math) instead of MUFU.EX2;
-//   * the running maximum is only raised when it grows by more than 2^8 (lazy rescale), so the O
-//     accumulator is almost never touched between PV MMAs;
+//   * NO row maximum at all in the kernel that normally runs (attn_fwd_kernel<.., true>, att_softmax_unshifted):
+//     P = 2^S straight from the accumulator, valid while the row sums stay within [2^-100, 2^100]; rows outside raise
+//     a flag and the launch is redone by the classic kernel (attn_fwd_kernel<.., false>: running maximum, raised only
+//     when it grows by more than 2^8 - lazy rescale - so that the O accumulator is almost never touched);
 //   * the two softmax warpgroups run unsynchronised: their exponential phases overlap partially and
 //     the loads / row-max / barrier phases of one hide under the MUFU work of the other (a strict
 //     ping-pong between them measured 5 % slower, four half-row warpgroups 15 % slower).
@@ -54,6 +56,8 @@ struct AttnParams {
   int num_items;        // regular + tail items
   long long* timing;    // debug (DSG_ATTN_TIMING builds): [grid][2 warpgroups][8] phase cycle totals
   int* hb;              // diagnostic heartbeat (see hb_mark), may be null
+  int* range_flag;      // device word shared by the two kernels of one attention launch (see attn_fwd_kernel)
+  int launch_id;        // != 0; what the unshifted kernel writes to *range_flag when a row leaves its range
 };
 
 #ifdef DSG_ATTN_TIMING
@@ -75,6 +79,10 @@ constexpr int ATT_THREADS = 128 + 2 * 32 * ATT_SMW;         // producer warpgrou
 #define DSG_ATTN_POLY_MASK 0x8080
 #endif
 constexpr unsigned ATT_POLY_MASK_QUADS = DSG_ATTN_POLY_MASK;
+#ifndef DSG_ATTN_POLY_MASK_UNSHIFTED
+#define DSG_ATTN_POLY_MASK_UNSHIFTED 0xA4A4
+#endif
+constexpr unsigned ATT_POLY_MASK_UNSHIFTED = DSG_ATTN_POLY_MASK_UNSHIFTED;   // the same for the kernel without row maxima
 constexpr int ATT_TILE_BYTES = 128 * ATT_DH * 2;  // 16 KB (Q, K or V tile)
 
 // Work items.  A regular item is a PAIR of 128-query tiles of one (frame, head): both warpgroups share one K/V
@@ -152,10 +160,32 @@ struct AttBars {
   uint64_t *s_full, *s_empty, *p_full, *pv_done;
 };
 
-// 2^(s*log2e + nmb) for two scores: MUFU.EX2, or (a fixed share of the pairs) the polynomial on the FMA / ALU pipes
-__device__ __forceinline__ float2 att_exp_pair(float s0, float s1, float2 l2e, float2 nmb, bool poly) {
-  const float2 x = ffma2(make_float2(s0, s1), l2e, nmb);
+// 2^(s - m) for two scores (s already in log2 units): MUFU.EX2, or (a fixed share of the pairs) the polynomial on the
+// FMA / ALU pipes.  SHIFT = false: the rows' reference maximum is 0 and the scores go to the exponential as they are
+// (att_softmax_unshifted).
+template <bool SHIFT>
+__device__ __forceinline__ float2 att_exp_pair(float s0, float s1, float2 nmb, bool poly) {
+  const float2 x = SHIFT ? fadd2(make_float2(s0, s1), nmb) : make_float2(s0, s1);
   return poly ? exp2_poly_x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+}
+
+// exponentials of one key tile: the thread's 64 scores -> 32 packed bf16 pairs + its share of the two row sums
+__device__ __forceinline__ void att_exp_tile(const uint32_t (&sr)[64], uint32_t (&pk)[32], float n0, float n1, float& add0,
+                                             float& add1) {
+  const float2 nmb0 = make_float2(-n0, -n0), nmb1 = make_float2(-n1, -n1);
+  float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
+  auto S = [&](int i) { return __uint_as_float(sr[i]); };
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float2 e0 = att_exp_pair<true>(S(4 * k), S(4 * k + 1), nmb0, (ATT_POLY_MASK_QUADS >> ((2 * k) & 15)) & 1);
+    const float2 e1 = att_exp_pair<true>(S(4 * k + 2), S(4 * k + 3), nmb1, (ATT_POLY_MASK_QUADS >> ((2 * k + 1) & 15)) & 1);
+    sum0 = fadd2(sum0, e0);
+    sum1 = fadd2(sum1, e1);
+    pk[2 * k] = pack_bf16x2(e0.x, e0.y);
+    pk[2 * k + 1] = pack_bf16x2(e1.x, e1.y);
+  }
+  add0 = sum0.x + sum0.y;
+  add1 = sum1.x + sum1.y;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -168,14 +198,12 @@ __device__ __forceinline__ float2 att_exp_pair(float s0, float s1, float2 l2e, f
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
                                                   const int warp, const int lane, const int num_tiles) {
-  constexpr float LOG2E = ATT_LOG2E;
   const int t = (warp - 4) >> 3;                   // query tile of this warp
   const int rbase = (warp & 3) * 32 + (((warp - 4) >> 2) & 1) * 16;   // first of the warp's 16 rows (= TMEM lanes)
   const int qd = lane & 3;                         // this thread's rows: rbase + lane / 4 and rbase + lane / 4 + 8
   // one TMEM base per warp (its 16 lanes, its query tile's columns); S / P / O are constant offsets from it
   const uint32_t t_addr = tmem_base + (uint32_t(rbase) << 16) + uint32_t(t) * ATT_T_COLS;
   const uint32_t s_addr = t_addr + ATT_S_OFF, p_addr = t_addr + ATT_P_OFF, o_addr = t_addr + ATT_O_OFF;
-  const float2 l2e = make_float2(LOG2E, LOG2E);
   // shared-memory address of this query tile's barriers, computed once (see mbar_wait_a): s_full[2], s_empty[2],
   // p_full[2], pv_done[2] are consecutive, so the four barriers of tile t are constant offsets from one register
   const uint32_t b_s_full = smem_u32(&bars.s_full[t]);
@@ -188,7 +216,7 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
     const int bh = t ? I.bh[1] : I.bh[0];
     const int h = bh % p.H, b = bh / p.H;
     const int q0 = t ? I.q0[1] : I.q0[0];
-    float m0 = 0.f, m1 = 0.f;                      // (stale) running maxima of this thread's two rows (raw scores)
+    float m0 = 0.f, m1 = 0.f;                      // reference maxima of this thread's two rows (log2 units)
     float l0 = 0.f, l1 = 0.f;                      // this thread's share of the running row sums of exp(s - m)
 
     for (int j = 0; j < num_tiles; ++j, ++sc) {
@@ -220,27 +248,18 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       // lazy rescale: the reference maximum of a row only moves when the row max has grown by more than 2^8
-      const bool g0 = j == 0 || (mx0 - m0) * LOG2E > ATT_RESCALE_THRESHOLD;
-      const bool g1 = j == 0 || (mx1 - m1) * LOG2E > ATT_RESCALE_THRESHOLD;
+      const bool g0 = j == 0 || mx0 - m0 > ATT_RESCALE_THRESHOLD;
+      const bool g1 = j == 0 || mx1 - m1 > ATT_RESCALE_THRESHOLD;
       const float n0 = g0 ? mx0 : m0, n1 = g1 ? mx1 : m1;
-      const float2 nmb0 = make_float2(-n0 * LOG2E, -n0 * LOG2E), nmb1 = make_float2(-n1 * LOG2E, -n1 * LOG2E);
-      float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
       uint32_t pk[32];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float2 e0 = att_exp_pair(S(4 * k), S(4 * k + 1), l2e, nmb0, (ATT_POLY_MASK_QUADS >> ((2 * k) & 15)) & 1);
-        const float2 e1 = att_exp_pair(S(4 * k + 2), S(4 * k + 3), l2e, nmb1, (ATT_POLY_MASK_QUADS >> ((2 * k + 1) & 15)) & 1);
-        sum0 = fadd2(sum0, e0);
-        sum1 = fadd2(sum1, e1);
-        pk[2 * k] = pack_bf16x2(e0.x, e0.y);
-        pk[2 * k + 1] = pack_bf16x2(e1.x, e1.y);
-      }
+      float add0, add1;
+      att_exp_tile(sr, pk, n0, n1, add0, add1);
       if (j > 0) {
         // PV_t(j-1) must have retired before P_t is overwritten or O_t is rescaled
         mbar_wait_a(b_pv_done, (sc - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, g0 || g1)) {
-          const float a0 = fast_exp2((m0 - n0) * LOG2E), a1 = fast_exp2((m1 - n1) * LOG2E);   // 1 for rows that keep m
+          const float a0 = fast_exp2(m0 - n0), a1 = fast_exp2(m1 - n1);   // 1 for rows that keep m
           uint32_t o[32];
           tmem_ld_16x256b_x8(o_addr, o);
           tmem_ld_wait();
@@ -258,8 +277,8 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
       }
       m0 = n0;
       m1 = n1;
-      l0 += sum0.x + sum0.y;
-      l1 += sum1.x + sum1.y;
+      l0 += add0;
+      l1 += add1;
       tmem_st_16x128b_x16(p_addr, pk);
       tmem_st_wait();
       tc_fence_before();
@@ -300,11 +319,138 @@ __device__ __forceinline__ void att_softmax_quads(const AttnParams& p, const uin
   }
 }
 
-template <int KV_STAGES>
+// ---------------------------------------------------------------------------------------------------------------
+// The same softmax WITHOUT any row maximum (attn_fwd_kernel<.., true>): every row keeps the reference 0, P = 2^S as the
+// tensor pipe wrote S.  No row-max pass, no shuffles, no subtraction: 2 MUFU + 1 packed add + 1 pack per pair of scores.
+// The scores are pulled from TMEM in four 32-column chunks, each processed while the next one is in flight: the
+// tcgen05.wait::ld between them keeps the instruction scheduler from hoisting all exponentials to the front (a warp
+// that has queued a burst of MUFU.EX2 cannot issue its FMA-pipe work behind them; with the chunks the two interleave).
+// Valid as long as every row sum stays inside [2^-100, 2^100] (row maximum within about +-88 log2 units, i.e. logits
+// within +-60): checked per row at the end of the work item.  A row outside raises *range_flag and the launch is
+// redone by the shifted kernel, which is enqueued behind this one and otherwise returns at once.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CH, bool MASK>
+__device__ __forceinline__ void att_exp_chunk(uint32_t (&c)[16], uint32_t* pk, float2& sum0, float2& sum1, int key0, int N) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (MASK) {                                    // last key tile of a ragged sequence: keys >= N do not exist
+      const int key = key0 + 8 * k;
+      if (key >= N) c[4 * k] = c[4 * k + 2] = 0xff800000u;          // -inf
+      if (key + 1 >= N) c[4 * k + 1] = c[4 * k + 3] = 0xff800000u;
+    }
+    constexpr float2 z = {0.f, 0.f};
+    const int kk = 4 * CH + k;
+    const float2 e0 = att_exp_pair<false>(__uint_as_float(c[4 * k]), __uint_as_float(c[4 * k + 1]), z,
+                                          (ATT_POLY_MASK_UNSHIFTED >> ((2 * kk) & 15)) & 1);
+    const float2 e1 = att_exp_pair<false>(__uint_as_float(c[4 * k + 2]), __uint_as_float(c[4 * k + 3]), z,
+                                          (ATT_POLY_MASK_UNSHIFTED >> ((2 * kk + 1) & 15)) & 1);
+    sum0 = fadd2(sum0, e0);
+    sum1 = fadd2(sum1, e1);
+    pk[2 * k] = pack_bf16x2(e0.x, e0.y);
+    pk[2 * k + 1] = pack_bf16x2(e1.x, e1.y);
+  }
+}
+
+template <bool MASK>
+__device__ __forceinline__ void att_exp_tile_chunked(uint32_t s_addr, uint32_t b_s_empty, uint32_t (&pk)[32], float2& sum0,
+                                                     float2& sum1, int key0, int N) {
+  uint32_t ca[16], cb[16];
+  tmem_ld_16x256b_x4(s_addr, ca);
+  tmem_ld_wait();
+  tmem_ld_16x256b_x4(s_addr + 32, cb);
+  att_exp_chunk<0, MASK>(ca, pk, sum0, sum1, key0, N);
+  tmem_ld_wait();
+  tmem_ld_16x256b_x4(s_addr + 64, ca);
+  att_exp_chunk<1, MASK>(cb, pk + 8, sum0, sum1, key0 + 32, N);
+  tmem_ld_wait();
+  tmem_ld_16x256b_x4(s_addr + 96, cb);
+  att_exp_chunk<2, MASK>(ca, pk + 16, sum0, sum1, key0 + 64, N);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive_a(b_s_empty);                        // the tensor pipe may overwrite S_t with the next scores
+  att_exp_chunk<3, MASK>(cb, pk + 24, sum0, sum1, key0 + 96, N);
+}
+
+__device__ __forceinline__ void att_softmax_unshifted(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
+                                                      const int warp, const int lane, const int num_tiles) {
+  const int t = (warp - 4) >> 3;
+  const int rbase = (warp & 3) * 32 + (((warp - 4) >> 2) & 1) * 16;
+  const int qd = lane & 3;
+  const uint32_t t_addr = tmem_base + (uint32_t(rbase) << 16) + uint32_t(t) * ATT_T_COLS;
+  const uint32_t s_addr = t_addr + ATT_S_OFF, p_addr = t_addr + ATT_P_OFF, o_addr = t_addr + ATT_O_OFF;
+  const uint32_t b_s_full = smem_u32(&bars.s_full[t]);
+  const uint32_t b_s_empty = b_s_full + 16, b_p_full = b_s_full + 32, b_pv_done = b_s_full + 48;
+  uint32_t sc = 0;
+  bool out_of_range = false;
+
+  for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    const AttItem I = att_decode(p, item);
+    if (t == 1 && !I.act1) continue;
+    const int bh = t ? I.bh[1] : I.bh[0];
+    const int h = bh % p.H, b = bh / p.H;
+    const int q0 = t ? I.q0[1] : I.q0[0];
+    float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);   // this thread's share of its two row sums
+
+    for (int j = 0; j < num_tiles; ++j, ++sc) {
+      mbar_wait_a(b_s_full, sc & 1);
+      tc_fence_after();
+      uint32_t pk[32];
+      const int kbase = j * ATT_BN;
+      if (kbase + ATT_BN > p.N) att_exp_tile_chunked<true>(s_addr, b_s_empty, pk, sum0, sum1, kbase + 2 * qd, p.N);
+      else att_exp_tile_chunked<false>(s_addr, b_s_empty, pk, sum0, sum1, 0, 0);
+      if (j > 0) {
+        mbar_wait_a(b_pv_done, (sc - 1) & 1);      // PV_t(j-1) must have retired before P_t is overwritten
+        tc_fence_after();
+      }
+      tmem_st_16x128b_x16(p_addr, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_a(b_p_full);
+    }
+
+    mbar_wait_a(b_pv_done, (sc - 1) & 1);
+    tc_fence_after();
+    float l0 = sum0.x + sum0.y, l1 = sum1.x + sum1.y;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // (written so that a NaN sum counts as out of range)
+    out_of_range |= !(l0 >= 0x1p-100f && l0 <= 0x1p100f) || !(l1 >= 0x1p-100f && l1 <= 0x1p100f);
+    const int r = lane & 15, ch = lane >> 4;
+    const float la = __shfl_sync(0xffffffffu, l0, 4 * (r & 7)), lb = __shfl_sync(0xffffffffu, l1, 4 * (r & 7));
+    const float inv_l = 1.0f / (r < 8 ? la : lb);
+    uint32_t o[32];
+    tmem_ld_16x32bx2_x32(o_addr, o);
+    tmem_ld_wait();
+    const int q = q0 + rbase + r;
+    if (q < p.N) {
+      __nv_bfloat16* dst = p.out + (size_t(b) * p.N + q) * p.D + h * ATT_DH + ch * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+        v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + i) = v;
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  if (out_of_range && p.range_flag != nullptr) *reinterpret_cast<volatile int*>(p.range_flag) = p.launch_id;
+}
+
+template <int KV_STAGES, bool UNSHIFTED>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t ATT_ARRIVALS = 32 * ATT_SMW;   // s_empty / p_full: one arrival per softmax thread of the query tile
+
+  // The shifted kernel doubles as the redo of an unshifted launch whose scores left the range (att_softmax_unshifted):
+  // it is enqueued behind it with the same launch_id and has nothing to do unless that launch raised the flag.
+  if (!UNSHIFTED && p.range_flag != nullptr && *reinterpret_cast<volatile int*>(p.range_flag) != p.launch_id) return;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -326,7 +472,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int lane = threadIdx.x & 31;
   const int num_tiles = (p.N + ATT_BN - 1) / ATT_BN;
 
-  constexpr int HB_CODE = 300 + ATT_SMW;
+  constexpr int HB_CODE = 300 + ATT_SMW + (UNSHIFTED ? 10 : 0);
   hb_mark(p.hb, HB_CODE, 1);
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQKV);
@@ -470,7 +616,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     // ------------------------------ softmax warps ------------------------------
     const AttBars ab{s_full, s_empty, p_full, pv_done};
     setmaxnreg_inc<ATT_QUAD_SOFTMAX_REGS>();
-    att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
+    if (UNSHIFTED) att_softmax_unshifted(p, tmem_base, ab, warp, lane, num_tiles);
+    else att_softmax_quads(p, tmem_base, ab, warp, lane, num_tiles);
   }
 
   hb_mark(p.hb, HB_CODE, 3);

@@ -289,15 +289,28 @@ void attn_plan_items(AttnParams& p) {
   p.num_items = p.B * p.H * p.full_pairs + (p.lone ? (p.B * p.H + 1) / 2 : 0);
 }
 
-cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s) {
-  p.timing = g_attn_timing;
-  p.hb = g_heartbeat;
-  attn_plan_items(p);
-  auto kern = attn_fwd_kernel<kAttnStages>;
+// One device word per attention launch (slot = launch id mod 256) through which the unshifted kernel tells the shifted
+// one, enqueued right behind it, that it has to redo the launch (attention.cuh, att_softmax_unshifted).
+int* attn_range_flags(int dev) {
+  static int* flags[64] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  int*& f = flags[dev & 63];
+  if (f == nullptr) {
+    if (cudaMalloc(&f, 256 * sizeof(int)) != cudaSuccess) { f = nullptr; return nullptr; }
+    cudaMemset(f, 0, 256 * sizeof(int));
+  }
+  return f;
+}
+std::atomic<int> g_attn_launch_id{0};
+int* g_attn_last_flag = nullptr;
+int g_attn_last_id = 0;
+
+template <bool UNSHIFTED>
+cudaError_t launch_attention_kernel(const CUtensorMap& qkv, const AttnParams& p, int num_sms, int dev, cudaStream_t s) {
+  auto kern = attn_fwd_kernel<kAttnStages, UNSHIFTED>;
   constexpr size_t smem = attn_smem_bytes<kAttnStages>();
   static bool attr[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
   if (!attr[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
@@ -306,6 +319,29 @@ cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, 
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;  // persistent: one CTA per SM
   kern<<<grid, ATT_THREADS, smem, s>>>(qkv, p);
   return cudaGetLastError();
+}
+
+// unshifted = true: the kernel without row maxima, followed by the classic one as its (normally empty) redo
+cudaError_t launch_attention(const CUtensorMap& qkv, AttnParams p, int num_sms, cudaStream_t s, bool unshifted = true) {
+  p.timing = g_attn_timing;
+  p.hb = g_heartbeat;
+  attn_plan_items(p);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  p.range_flag = nullptr;
+  p.launch_id = 0;
+  if (!unshifted) return launch_attention_kernel<false>(qkv, p, num_sms, dev, s);
+  int* flags = attn_range_flags(dev);
+  if (flags == nullptr) return cudaErrorMemoryAllocation;
+  int id = ++g_attn_launch_id;
+  if (id <= 0) { g_attn_launch_id = 1; id = 1; }
+  p.range_flag = flags + (id & 255);
+  p.launch_id = id;
+  g_attn_last_flag = p.range_flag;
+  g_attn_last_id = id;
+  cudaError_t e = launch_attention_kernel<true>(qkv, p, num_sms, dev, s);
+  if (e != cudaSuccess) return e;
+  return launch_attention_kernel<false>(qkv, p, num_sms, dev, s);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int M, int D, float eps,
@@ -530,6 +566,7 @@ struct dinoseg {
   int debug_stop = 0;
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
+  bool attn_unshifted = true;       // attention without row maxima + the classic kernel as its redo (attention.cuh)
   bool fuse_ln = true;              // ... which also computes LayerNorm2 itself (no LN launch, no bf16 copy of the tokens)
   bool weights_dirty = true;        // fc1_w / fc1_b have to be (re)derived from the loaded parameters
   bool folded = false;              // ... and currently carry LayerNorm2's gamma / beta
@@ -739,6 +776,7 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0 ? 1 : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_FUSE_LN")) h->fuse_ln = atoi(mode) != 0;         // measurement override
+  if (const char* mode = getenv("DINOSEG_ATTN_UNSHIFTED")) h->attn_unshifted = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_HOST_CHUNK")) h->host_chunk = atoi(mode) > 0 ? atoi(mode) : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_MLP_MODE")) {   // measurement override: 0 unfused, 1 fused, 2 fused as CTA pairs
@@ -1133,7 +1171,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
     {
       GemmParams p = gp(3 * D, D, b.qkv_b);
       p.reverse = h->reverse_order;              // LN1 wrote abuf first-to-last
-      p.col_scale = 0.125f; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85)
+      p.col_scale = 0.125f * ATT_LOG2E; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85), times log2(e): attention.cuh
       LaunchScope ls(h, K_GEMM_QKV, s);
       if (h->gemm_pair &&
           launch_gemm_pair<EPI_BF16>(w.tm_abuf, b.tm_qkv_h, w.tm_qkv_out, w.tm_qkv_out, p, sms, s) != cudaSuccess) {
@@ -1148,7 +1186,7 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
       AttnParams p{};
       p.B = batch; p.H = H; p.N = h->Ntok; p.D = D; p.out = w.abuf;
       LaunchScope ls(h, K_ATTN, s);
-      DSG_CUDA(h, launch_attention(w.tm_qkv3d, p, h->num_sms, s)); ++n;
+      DSG_CUDA(h, launch_attention(w.tm_qkv3d, p, h->num_sms, s, h->attn_unshifted)); n += h->attn_unshifted ? 2 : 1;
     }
     {
       GemmParams p = gp(D, D, b.proj_b);
@@ -1866,7 +1904,16 @@ int dinoseg_op_attention(const void* qkv, void* out, int B, int N, int H, void* 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return launch_attention(tq, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
+  const char* mode = getenv("DINOSEG_ATTN_UNSHIFTED");
+  return launch_attention(tq, p, sms, static_cast<cudaStream_t>(stream), mode == nullptr || atoi(mode) != 0) == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_debug_attn_redone(void) {
+  if (g_attn_last_flag == nullptr) return 0;
+  int v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, g_attn_last_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v == g_attn_last_id ? 1 : 0;
 }
 
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps,

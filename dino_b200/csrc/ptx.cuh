@@ -411,6 +411,17 @@ __device__ __forceinline__ void tmem_ld_16x256b_x16(uint32_t taddr, uint32_t (&r
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 32 columns: thread (r = lane/4, q = lane%4) gets, of every 8-column group k, columns 8k+2q, 8k+2q+1 of
+// rows r (registers 4k, 4k+1) and r+8 (registers 4k+2, 4k+3)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.16x256b.x8.b32 "

@@ -189,8 +189,12 @@ int dinoseg_op_gemm(const void* A_bf16, const void* W_bf16, const float* bias, v
  * tiles, the W tile split between the two SMs) - how the qkv GEMM (and ViT-B's fc1 / fc2) of the forward are launched */
 int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo, int epi,
                          float col_scale, int scale_cols, void* stream);
-/* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16 (q pre-scaled) */
+/* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16; q carries dh^-0.5 * log2(e) already (the qkv GEMM's
+ * epilogue applies it), i.e. the kernel computes P = 2^(q k^T) */
 int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int H, void* stream);
+/* Test hook: synchronises the device; 1 if the process's most recent attention launch left the range of the kernel
+ * without row maxima and was redone by the classic kernel, 0 if not, -1 on a CUDA error. */
+int dinoseg_debug_attn_redone(void);
 /* Test hook (pure CPU): worker pool of the host entry points with n threads where the creation of thread fail_at fails
  * (< 0: none); returns the threads the pool ended up with (0: none, the caller falls back to the DMA path), -1 on error. */
 int dinoseg_debug_host_pool(int n, int fail_at);

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-so = os.environ.get("DSG_TIMING_SO", os.path.join(ROOT, "tools", "ubench", "libdinoseg_timing.so"))
+so = os.environ.get("DSG_TIMING_SO", os.path.join(ROOT, "dino_b200", "lib", "libdinoseg.so"))
 names = ["wait s_full", "tmem ld S", "row max", "wait pv_done (+rescale)", "ping-pong wait", "exp phase",
          "st wait + p_full", "loop/epilogue/other"]
 
@@ -21,7 +21,7 @@ def main():
     B, N, H = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 3601, 6
     D = H * 64
     qkv = (torch.randn(B, N, 3 * D, device="cuda") * 1.0)
-    qkv[..., :D] *= 0.125
+    qkv[..., :D] *= 0.125 * 1.4426950408889634
     qkv = qkv.to(torch.bfloat16)
     out = torch.zeros(B * N, D, device="cuda", dtype=torch.bfloat16)
     timing = torch.zeros(148 * 3 * 8, dtype=torch.int64, device="cuda")

@@ -126,23 +126,26 @@ def check_gemm_pair(name, M, N, K, epi=0):
                    identical_to_single_cta=same, n_bad=int(bad.shape[0]), first_bad=bad[0].tolist() if bad.numel() else None)
 
 
-def check_attention(name, B, N, H):
+def check_attention(name, B, N, H, spread=1.0, shift=0.0, redone=0):
     torch, L, lib = _imports()
     torch.manual_seed(2)
     dev = "cuda"
     D = H * 64
     qkv = torch.randn(B, N, 3 * D, device=dev)
-    qkv[..., :D] *= 0.125 * 2.0  # pre-scaled q with a bit more spread than unit variance
+    qkv[..., :D] *= 0.125 * 2.0 * spread  # pre-scaled q (dh^-0.5 * log2 e folded in) with more spread than unit variance
+    qkv[..., D:2 * D] += shift                 # a common offset of the keys moves whole rows of scores
     qkv = qkv.to(torch.bfloat16)
     out = torch.zeros(B * N, D, device=dev, dtype=torch.bfloat16)
     rc = lib.dinoseg_op_attention(_ptr(qkv), _ptr(out), B, N, H, None)
     torch.cuda.synchronize()
+    # which kernel produced the result: the one without row maxima, or (scores out of its range) the classic one as its redo
+    was_redone = lib.dinoseg_debug_attn_redone() if os.environ.get("DINOSEG_ATTN_UNSHIFTED", "1") != "0" else redone
     f = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     q, k, v = f[0], f[1], f[2]
     ref = torch.empty(B, H, N, 64, device=dev)
     for b in range(B):
         for h in range(H):
-            s = q[b, h] @ k[b, h].t()
+            s = (q[b, h] @ k[b, h].t()) * math.log(2.0)   # the kernel's scores are in log2 units
             ref[b, h] = torch.softmax(s, dim=-1) @ v[b, h]
     ref = ref.permute(0, 2, 1, 3).reshape(B * N, D)
     got = out.float()
@@ -151,8 +154,8 @@ def check_attention(name, B, N, H):
     tol = 2.5e-2 * scale
     bad = ((got - ref).abs() > tol).nonzero()
     first_bad = bad[0].tolist() if bad.numel() else None
-    return _report(name, rc == 0 and err <= tol and bool(torch.isfinite(got).all()), rc=rc, max_abs_err=err,
-                   ref_absmax=scale, tol=tol, n_bad=int(bad.shape[0]), first_bad=first_bad)
+    return _report(name, rc == 0 and err <= tol and bool(torch.isfinite(got).all()) and was_redone == redone, rc=rc, max_abs_err=err,
+                   ref_absmax=scale, tol=tol, n_bad=int(bad.shape[0]), first_bad=first_bad, redone=was_redone)
 
 
 def check_mlp(name, M, pair=0):
@@ -327,6 +330,11 @@ def _checks():
         "attn_901": lambda: check_attention("attn_901", 2, 901, 6),
         "attn_3601": lambda: check_attention("attn_3601", 1, 3601, 6),
         "attn_vitb_901": lambda: check_attention("attn_vitb_901", 1, 901, 12),
+        # scores beyond +-100 log2 units: the kernel without row maxima flags the launch and the classic kernel redoes it
+        "attn_wide_901": lambda: check_attention("attn_wide_901", 2, 901, 6, spread=16.0, redone=1),
+        "attn_shifted_901": lambda: check_attention("attn_shifted_901", 2, 901, 6, spread=4.0, shift=6.0, redone=1),
+        # logits up to about +-60: large, but still inside the range of the kernel without row maxima
+        "attn_spread8_901": lambda: check_attention("attn_spread8_901", 2, 901, 6, spread=8.0),
         "mlp_1block": lambda: check_mlp("mlp_1block", 128),
         "mlp_ragged": lambda: check_mlp("mlp_ragged", 901),
         "mlp_multi": lambda: check_mlp("mlp_multi", 148 * 128 * 2 + 77),
