@@ -549,7 +549,8 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logprobs, uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------
-// CLS-query attention of one block: out[b, h, j] = softmax_j( q_cls(b,h) . k_j(b,h) )      (q pre-scaled by dh^-0.5)
+// CLS-query attention of one block: out[b, h, j] = softmax_j( q_cls(b,h) . k_j(b,h) )
+// (q as the qkv GEMM wrote it, pre-scaled by dh^-0.5 * log2(e): the scores are in log2 units, attention.cuh)
 // = row 0 of the attention matrix VisionTransformer.get_last_selfattention returns (reference
 // vision_transformer.py:273-280, :85-101), the only row its caller uses (visualize_attention.py:46-54).
 // qkv: [B, N, 3D] bf16 as written by the qkv GEMM.  One CTA per (b, h); N x 64 dot products are nothing next to
@@ -596,7 +597,7 @@ cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ 
   mx = bcast;
   float sum = 0.f;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    const float e = expf(o[j] - mx);
+    const float e = exp2f(o[j] - mx);
     o[j] = e;
     sum += e;
   }

@@ -447,6 +447,13 @@ __device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_
       "r"(taddr)
       : "memory");
 }
+// 16 lanes x 16 columns (registers 8c .. 8c+7 of the .x16 form below, columns 16c .. 16c+15)
+__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x4.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_16x128b_x16(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.16x128b.x16.b32 [%32], "

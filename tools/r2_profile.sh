@@ -22,7 +22,7 @@ say "ncu --set full: attention kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 4 -c 1 -o gpurun_out/r02_attn $CMD > gpurun_out/r02_ncu2.log 2>&1
 say "rc=$?"
 say "ncu --set full: one whole step"
-NK=${STEP_KERNELS:-19}
+NK=${STEP_KERNELS:-23}
 timeout 1200 ncu --set full --clock-control none -k regex:'gemm_bf16|mlp_fused|layernorm|head_|im2col|attn_fwd|cls_row' -s $((3 * NK)) -c $NK -o gpurun_out/r02_step $CMD > gpurun_out/r02_ncu3.log 2>&1
 say "rc=$?"
 ls -la gpurun_out/r02_*.ncu-rep
