@@ -239,6 +239,46 @@ cudaError_t launch_gemm_pair_t(const CUtensorMap& a, const CUtensorMap& w, const
   return cudaLaunchKernelEx(&cfg, kern, a, w, out, add, pp);
 }
 
+// CTA-pair GEMM with the LayerNorm of fp32 rows as its A operand (gemm.cuh, LN_A): K = 384, resident A produced in place.
+// `w` (96-row boxes) and p.bias must carry the LayerNorm's gamma / beta (fold_ln_weight_kernel).
+template <int EPI>
+cudaError_t launch_gemm_pair_ln(const float* x, float eps, const CUtensorMap& w, const CUtensorMap& out, const GemmParams& p,
+                                int num_sms, cudaStream_t s) {
+  auto kern = gemm_bf16_tn_kernel<EPI, true, true, true>;
+  constexpr size_t smem = gemm_smem_bytes(EPI, true, true);
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
+  const int m_tiles = (p.rows_per_batch + GEMM_BM - 1) / GEMM_BM;
+  const long long units = (m_tiles + 1) / 2;
+  if (x == nullptr || units <= 0 || p.K != GEMM_RES_KB * GEMM_BK || p.batches != 1 || p.a_wrap != 0 ||
+      n_tiles * GEMM_BN > GEMM_LN_STATS_OFF)
+    return cudaErrorInvalidValue;
+  const int max_pairs = num_sms / 2;
+  GemmParams pp = p;
+  pp.timing = g_attn_timing;
+  pp.hb = g_heartbeat;
+  pp.ln_x = x;
+  pp.ln_eps = eps;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * unsigned(units < max_pairs ? units : max_pairs));
+  cfg.blockDim = dim3(GEMM_THREADS + GEMM_LN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, w, w, out, out, pp);   // (the A tensor map is not used)
+}
+
 template <int EPI>
 cudaError_t launch_gemm_pair(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& add,
                              const GemmParams& p, int num_sms, cudaStream_t s) {
@@ -400,6 +440,11 @@ struct BlockW {
   // fc1 as loaded (fp32): fc1_w / fc1_b above are derived from these by finalize_weights - plain bf16 / copy, or with
   // LayerNorm2's gamma / beta folded in when the fused MLP kernel computes the LayerNorm itself
   float *fc1_w32 = nullptr, *fc1_b32 = nullptr;
+  // qkv: the loaded fp32 weight; qkv_w = its bf16 copy; qkv_wf / qkv_bf = with LayerNorm1's gamma / beta folded in, for
+  // the qkv GEMM that computes the LayerNorm itself (launch_gemm_pair_ln)
+  float *qkv_w32 = nullptr, *qkv_bf = nullptr;
+  __nv_bfloat16* qkv_wf = nullptr;
+  CUtensorMap tm_qkv_hf;
   CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
   CUtensorMap tm_fc1_g, tm_fc2_g;   // 128-row granule views for the fused MLP kernel
   CUtensorMap tm_fc1_h, tm_fc2_h;   // 64-row half granules (CTA-pair variant)
@@ -567,6 +612,7 @@ struct dinoseg {
   int launches = 0;
   bool fused_mlp = false;           // D = 384 / hidden = 1536: fused fc1 -> GELU -> fc2 kernel
   bool attn_unshifted = true;       // attention without row maxima + the classic kernel as its redo (attention.cuh)
+  bool fuse_ln1 = false;            // ViT-S: LayerNorm1 computed by the qkv GEMM (CTA pairs) instead of its own kernel (opt-in)
   bool fuse_ln = true;              // ... which also computes LayerNorm2 itself (no LN launch, no bf16 copy of the tokens)
   bool weights_dirty = true;        // fc1_w / fc1_b have to be (re)derived from the loaded parameters
   bool folded = false;              // ... and currently carry LayerNorm2's gamma / beta
@@ -776,6 +822,12 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
   if (const char* mode = getenv("DINOSEG_HOST_EXPAND")) h->host_expand = atoi(mode) != 0 ? 1 : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_REVERSE")) h->reverse_order = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_FUSE_LN")) h->fuse_ln = atoi(mode) != 0;         // measurement override
+  // LayerNorm1 inside the qkv GEMM is OFF by default: measured neutral (LayerNorm 0.086 + qkv 0.181 ms per block against
+  // 0.256-0.265 ms fused).  The fused kernel reads the fp32 rows twice (statistics, then the normalised block) on top of
+  // the W tiles - 834 KB per row block and SM through the ~42 B/clk L2 -> SM path against 540 KB - and turns from
+  // MMA-bound into delivery-bound.  DINOSEG_FUSE_LN1=1 selects it (parity-tested: gemm_ln_* checks).
+  h->fuse_ln1 = false;
+  if (const char* mode = getenv("DINOSEG_FUSE_LN1")) h->fuse_ln1 = cfg->embed_dim == GEMM_RES_KB * GEMM_BK && atoi(mode) != 0;
   if (const char* mode = getenv("DINOSEG_ATTN_UNSHIFTED")) h->attn_unshifted = atoi(mode) != 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_HOST_CHUNK")) h->host_chunk = atoi(mode) > 0 ? atoi(mode) : 0;   // measurement override
   if (const char* mode = getenv("DINOSEG_GEMM_PAIR")) h->gemm_pair = atoi(mode) != 0;   // measurement override
@@ -825,6 +877,8 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     rc |= dev_alloc(h, &b.ln1_g, D); rc |= dev_alloc(h, &b.ln1_b, D);
     rc |= dev_alloc(h, &b.ln2_g, D); rc |= dev_alloc(h, &b.ln2_b, D);
     rc |= dev_alloc(h, &b.qkv_w, size_t(3) * D * D); rc |= dev_alloc(h, &b.qkv_b, 3 * D);
+    rc |= dev_alloc(h, &b.qkv_w32, size_t(3) * D * D); rc |= dev_alloc(h, &b.qkv_wf, size_t(3) * D * D);
+    rc |= dev_alloc(h, &b.qkv_bf, 3 * D);
     rc |= dev_alloc(h, &b.proj_w, size_t(D) * D); rc |= dev_alloc(h, &b.proj_b, D);
     rc |= dev_alloc(h, &b.fc1_w, size_t(HID) * D); rc |= dev_alloc(h, &b.fc1_b, HID);
     rc |= dev_alloc(h, &b.fc1_w32, size_t(HID) * D); rc |= dev_alloc(h, &b.fc1_b32, HID);
@@ -832,13 +886,14 @@ int dinoseg_create(const dinoseg_cfg* cfg, int device, dinoseg_t** out) {
     if (rc) break;
     add_slot(h, pre + "norm1.weight", 0, b.ln1_g, {D}); add_slot(h, pre + "norm1.bias", 0, b.ln1_b, {D});
     add_slot(h, pre + "norm2.weight", 0, b.ln2_g, {D}); add_slot(h, pre + "norm2.bias", 0, b.ln2_b, {D});
-    add_slot(h, pre + "attn.qkv.weight", 1, b.qkv_w, {3 * D, D}); add_slot(h, pre + "attn.qkv.bias", 0, b.qkv_b, {3 * D});
+    add_slot(h, pre + "attn.qkv.weight", 0, b.qkv_w32, {3 * D, D}); add_slot(h, pre + "attn.qkv.bias", 0, b.qkv_b, {3 * D});
     add_slot(h, pre + "attn.proj.weight", 1, b.proj_w, {D, D}); add_slot(h, pre + "attn.proj.bias", 0, b.proj_b, {D});
     add_slot(h, pre + "mlp.fc1.weight", 0, b.fc1_w32, {HID, D}); add_slot(h, pre + "mlp.fc1.bias", 0, b.fc1_b32, {HID});
     add_slot(h, pre + "mlp.fc2.weight", 1, b.fc2_w, {D, HID}); add_slot(h, pre + "mlp.fc2.bias", 0, b.fc2_b, {D});
     bool ok = true;
     ok &= make_tmap_2d(&b.tm_qkv, b.qkv_w, 3 * D, D, D, GEMM_BN);
     ok &= make_tmap_2d(&b.tm_qkv_h, b.qkv_w, 3 * D, D, D, GEMM_BN / 2);
+    ok &= make_tmap_2d(&b.tm_qkv_hf, b.qkv_wf, 3 * D, D, D, GEMM_BN / 2);
     ok &= make_tmap_2d(&b.tm_fc1_p, b.fc1_w, HID, D, D, GEMM_BN / 2);
     ok &= make_tmap_2d(&b.tm_fc2_p, b.fc2_w, D, HID, HID, GEMM_BN / 2);
     ok &= make_tmap_2d(&b.tm_proj, b.proj_w, D, D, D, GEMM_BN);
@@ -1057,6 +1112,13 @@ static int finalize_weights(dinoseg_t* h, cudaStream_t s) {
   if (!h->weights_dirty && h->folded == fold) return 0;
   const int D = h->cfg.embed_dim, HID = h->cfg.mlp_hidden;
   for (BlockW& b : h->blocks) {
+    {                                              // qkv: plain bf16 copy, and the form with LayerNorm1 folded in
+      const size_t n = size_t(3) * D * D;
+      f32_to_bf16_kernel<<<unsigned(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, s>>>(b.qkv_w32, b.qkv_w, n);
+      fold_ln_weight_kernel<<<(3 * D * 32 + 255) / 256, 256, 0, s>>>(b.qkv_w32, b.qkv_b, b.ln1_g, b.ln1_b, b.qkv_wf, b.qkv_bf,
+                                                                     3 * D, D);
+      DSG_CUDA(h, cudaGetLastError());
+    }
     if (fold) {
       fold_ln_weight_kernel<<<(HID * 32 + 255) / 256, 256, 0, s>>>(b.fc1_w32, b.fc1_b32, b.ln2_g, b.ln2_b, b.fc1_w, b.fc1_b,
                                                                    HID, D);
@@ -1167,8 +1229,22 @@ static int forward_impl(dinoseg_t* h, WorkBufs& w, const float* frames, const ui
   // ---- transformer blocks (vision_transformer.py:122-140) ----
   for (int i = 0; i < h->cfg.n_blocks; ++i) {
     BlockW& b = h->blocks[i];
-    { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln1_g, b.ln1_b, w.abuf, M, D, eps, false, s)); ++n; }
-    {
+    bool ln1_done = false;
+    if (h->fuse_ln1 && h->gemm_pair) {
+      // LayerNorm1 -> qkv in ONE kernel: the GEMM's extra warps normalise the fp32 tokens straight into its A block
+      GemmParams p = gp(3 * D, D, b.qkv_bf);
+      p.reverse = h->reverse_order ? 0 : 1;      // the producer of x (fc2 epilogue / patch GEMM) wrote it first-to-last
+      p.col_scale = 0.125f * ATT_LOG2E; p.scale_cols = D;
+      LaunchScope ls(h, K_GEMM_QKV, s);
+      if (launch_gemm_pair_ln<EPI_BF16>(w.x, eps, b.tm_qkv_hf, w.tm_qkv_out, p, sms, s) == cudaSuccess) {
+        ln1_done = true; ++n;
+      } else {
+        (void)cudaGetLastError();   // no 2-CTA clusters on this device / partition: LayerNorm kernel + plain GEMM
+        h->fuse_ln1 = false;
+      }
+    }
+    if (!ln1_done) { LaunchScope ls(h, K_LN, s); DSG_CUDA(h, launch_layernorm(w.x, b.ln1_g, b.ln1_b, w.abuf, M, D, eps, false, s)); ++n; }
+    if (!ln1_done) {
       GemmParams p = gp(3 * D, D, b.qkv_b);
       p.reverse = h->reverse_order;              // LN1 wrote abuf first-to-last
       p.col_scale = 0.125f * ATT_LOG2E; p.scale_cols = D;  // q * head_dim^-0.5 (vision_transformer.py:73,85), times log2(e): attention.cuh
@@ -1760,6 +1836,23 @@ int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* 
                         : epi == EPI_GELU_BF16 ? launch_gemm_pair<EPI_GELU_BF16>(ta, tw, to, to, p, sms, s)
                                                : launch_gemm_pair<EPI_RESID_F32>(ta, tw, to, to, p, sms, s);
   return e == cudaSuccess ? 0 : -3;
+}
+
+int dinoseg_op_gemm_pair_ln(const float* x, const void* W, const float* bias, void* out, int M, int N, float eps,
+                            float col_scale, int scale_cols, void* stream) {
+  if (!x || !W || !out || M <= 0 || N <= 0 || N % 8 != 0) return -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int K = GEMM_RES_KB * GEMM_BK;
+  CUtensorMap tw, to;
+  GemmParams p{};
+  p.N = N; p.K = K; p.bias = bias; p.col_scale = col_scale; p.scale_cols = scale_cols;
+  p.rows_per_batch = M; p.batches = 1;
+  bool ok = make_tmap_2d(&tw, W, N, K, K, GEMM_BN / 2);
+  ok &= make_tmap_gemm_out(&to, out, false, N, M, 1, N);
+  if (!ok) return -2;
+  return launch_gemm_pair_ln<EPI_BF16>(x, eps, tw, to, p, sms, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -3;
 }
 
 // Test hook for the worker pool of the host entry points: create a pool of n threads where the creation of thread number

@@ -189,6 +189,11 @@ int dinoseg_op_gemm(const void* A_bf16, const void* W_bf16, const float* bias, v
  * tiles, the W tile split between the two SMs) - how the qkv GEMM (and ViT-B's fc1 / fc2) of the forward are launched */
 int dinoseg_op_gemm_pair(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, int ldo, int epi,
                          float col_scale, int scale_cols, void* stream);
+/* out[M, N] bf16 = (xhat W^T + bias) * (col < scale_cols ? col_scale : 1) with xhat = LayerNorm(x) WITHOUT its affine
+ * transform (x fp32 [M, 384]; gamma / beta folded into W / bias by dinoseg_op_fold_ln): the CTA-pair GEMM that
+ * normalises its own A operand - how norm1 -> qkv runs for ViT-S (reference vision_transformer.py:117, :133, :82) */
+int dinoseg_op_gemm_pair_ln(const float* x, const void* W_bf16, const float* bias, void* out_bf16, int M, int N, float eps,
+                            float col_scale, int scale_cols, void* stream);
 /* out[B*N, D] bf16 = softmax(q k^T) v over qkv[B, N, 3D] bf16; q carries dh^-0.5 * log2(e) already (the qkv GEMM's
  * epilogue applies it), i.e. the kernel computes P = 2^(q k^T) */
 int dinoseg_op_attention(const void* qkv_bf16, void* out_bf16, int B, int N, int H, void* stream);
