@@ -516,7 +516,8 @@ def main():
         ach = f_launch / (att_ms / att_n * 1e-3) / 1e12
         traffic, traffic_src, traffic_block = (ncu_attention_traffic() if (B, res, args.arch) == (64, 480, "vit_small")
                                                else (None, None, None))
-        roofline = {"kernel": "attn_fwd_kernel (fused QK^T -> softmax -> PV, tcgen05/TMEM)", "bound": "tensor",
+        roofline = {"kernel": "attn_fwd_kernel<6, true> (fused QK^T -> softmax without row maxima -> PV, tcgen05/TMEM) "
+                              "+ the empty launch of its range-redo twin, timed together", "bound": "tensor",
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     # the kernel is timed inside a step that keeps the GPU under load, hence `peak` = the SUSTAINED cuBLAS
                     # figure; the fraction of the burst figure (a kernel timed alone on a cool GPU) is given beside it

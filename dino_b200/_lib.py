@@ -83,6 +83,7 @@ SIGNATURES = {
     "dinoseg_half_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dinoseg_set_fused_mlp": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_set_fused_head": (C.c_int, [C.c_void_p, C.c_int]),
+    "dinoseg_set_fuse_ln1": (C.c_int, [C.c_void_p, C.c_int]),
     "dinoseg_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_float, C.c_void_p]),
     "dinoseg_op_posembed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -1930,6 +1930,13 @@ int dinoseg_set_fused_mlp(dinoseg_t* h, int on) {
   return 0;
 }
 
+int dinoseg_set_fuse_ln1(dinoseg_t* h, int on) {
+  if (!h) return -1;
+  if (on && h->cfg.embed_dim != GEMM_RES_KB * GEMM_BK) DSG_FAIL(h, "LayerNorm1 inside the qkv GEMM needs embed_dim 384");
+  h->fuse_ln1 = on != 0;
+  return 0;
+}
+
 int dinoseg_set_fused_head(dinoseg_t* h, int on) {
   if (!h) return -1;
   if (on && !(h->cfg.head_kind == 0 && h->cfg.embed_dim == HEAD_D && h->cfg.head_h1 <= HEAD_N1 && h->cfg.head_h2 <= HEAD_W3_PITCH - 4))

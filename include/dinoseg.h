@@ -232,6 +232,9 @@ int dinoseg_set_fused_mlp(dinoseg_t* h, int on);
 /* 1 (default where it applies: 'mlp' head, embed_dim 384): final LayerNorm -> layer_1 -> layer_2 -> layer_3 -> log_softmax
  * -> argmax -> p x p replication in ONE kernel (csrc/head.cuh); 0: the separate LayerNorm / GEMM / GEMM / tail kernels */
 int dinoseg_set_fused_head(dinoseg_t* h, int on);
+/* 1: LayerNorm1 of every block is computed by the qkv GEMM itself (CTA pairs, embed_dim 384 only) instead of its own kernel;
+ * off by default (measured neutral).  Same function, operands rounded to bf16 at the same points. */
+int dinoseg_set_fuse_ln1(dinoseg_t* h, int on);
 int dinoseg_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int M, int D,
                          float eps, void* stream);
 int dinoseg_op_posembed(const float* pos_src, float* out, int G0, int g, int D, void* stream);

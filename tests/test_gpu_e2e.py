@@ -479,6 +479,30 @@ def test_fused_head_matches_the_kernel_chain(variant, res, batch):
     assert torch.equal(low_only, low1) and torch.equal(lab_only, lab1)
 
 
+def test_layernorm1_inside_the_qkv_gemm_matches_the_two_kernel_path():
+    """Opt-in form of norm1 -> qkv (reference vision_transformer.py:117, :133, :82): the CTA-pair GEMM normalises the fp32
+    tokens itself (gamma / beta folded into the qkv weight) instead of reading the LayerNorm kernel's bf16 output.  Same
+    function with the same bf16 operand rounding, so the log-probs agree far inside the bf16-vs-fp32 tolerance."""
+    lib = _lib.load()
+    m, cfg, sd = _model("vit_small", 2, 21, "trained_like")
+    x = synthetic.make_frames(3, 240, seed=11).cuda()
+    lp0, low0, _ = m.infer(x, want_logprobs=True, want_lowres=True)
+    n0 = m.last_launch_count()
+    assert lib.dinoseg_set_fuse_ln1(m._handle, 1) == 0
+    try:
+        lp1, low1, _ = m.infer(x, want_logprobs=True, want_lowres=True)
+        n1 = m.last_launch_count()
+    finally:
+        assert lib.dinoseg_set_fuse_ln1(m._handle, 0) == 0
+    torch.cuda.synchronize()
+    assert n1 == n0 - 2                                            # one LayerNorm launch less per block
+    rng = float(lp0.max() - lp0.min())
+    d = float((lp1 - lp0).abs().max())
+    _record(case="fuse_ln1_240", max_abs_vs_two_kernels=d, range=rng)
+    assert d <= 5e-3 * max(1.0, rng), (d, rng)
+    assert float((low1 == low0).float().mean()) >= 0.995
+
+
 def test_weight_update_is_picked_up():
     """load_state_dict after the first forward re-packs the bf16 weights (no stale cache)."""
     m, cfg, sd = _model("vit_small", 1, 1, "reference_init")
