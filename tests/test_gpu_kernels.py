@@ -20,3 +20,12 @@ NAMES = list(gpu_check.check_names())
 @pytest.mark.parametrize("name", NAMES)
 def test_kernel(name):
     assert gpu_check.run_check(name)
+
+
+@pytest.mark.parametrize("unshifted", ["1", "0"])
+def test_attention_shape_sweep(unshifted, monkeypatch):
+    """Token counts around every tile boundary (1 .. 1153), odd numbers of (frame, head)s, 1 / 6 / 12 heads: the attention
+    kernel without row maxima (default) and its classic twin alone, each against fp32 torch (tools/attn_sweep.py)."""
+    import attn_sweep
+    monkeypatch.setenv("DINOSEG_ATTN_UNSHIFTED", unshifted)
+    assert attn_sweep.main() == 0
