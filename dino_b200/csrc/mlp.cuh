@@ -74,7 +74,10 @@ constexpr int MLP_CH = 128;                         // hidden columns per chunk
 constexpr int MLP_NCH = MLP_HID / MLP_CH;           // 12
 constexpr int MLP_KB = MLP_D / 64;                  // 6 k-blocks of A / W1 granules per chunk
 constexpr int MLP_GRAN = 128 * 64 * 2;              // 16 KB
-constexpr int MLP_RING = 4;
+#ifndef DSG_MLP_RING
+#define DSG_MLP_RING 4
+#endif
+constexpr int MLP_RING = DSG_MLP_RING;
 constexpr int MLP_LAG = 1;                          // MMA2(c) is issued right after MMA1(c + MLP_LAG) (a lag of 2 measured 25 % slower: single G buffer)
 constexpr int MLP_THREADS = 64 + 256 + 128;         // producer + MMA, 8 GELU warps, 4 output warps
 constexpr size_t MLP_SMEM = size_t(MLP_KB) * MLP_GRAN + 2 * MLP_GRAN + 2 * MLP_GRAN + size_t(MLP_RING) * MLP_GRAN + 1024 + 512 +

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-so = os.environ.get("DSG_TIMING_SO", os.path.join(ROOT, "tools", "ubench", "libdinoseg_mtiming.so"))
+so = os.environ.get("DSG_TIMING_SO", os.path.join(ROOT, "dino_b200", "lib", "libdinoseg.so"))
 MMA = ["wait w_full", "wait acc1_empty", "wait g_full", "wait a_full", "wait acc2_empty", "-", "-", "issue + other"]
 EPI = ["-", "wait acc1_full", "ld + gelu", "wait g_empty", "write G", "-", "-", "other"]
 
