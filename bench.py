@@ -501,7 +501,10 @@ def main():
         for _ in range(3):
             step()
         torch.cuda.synchronize()
+        span_ms, gap_ms = model.profile_gaps()        # first launch's start -> last launch's end, and the time between launches
         kinds = {k: {"ms_per_step": v[0] / 3, "launches_per_step": v[1] // 3} for k, v in model.profile_read().items()}
+        kinds["(between launches, incl. the event records)"] = {"ms_per_step": gap_ms / 3, "launches_per_step": 0}
+        kinds["(span of the 3 profiled steps / 3)"] = {"ms_per_step": span_ms / 3, "launches_per_step": 0}
         model.profile_enable(False)
 
     # ---- roofline of the dominant kernel: fused attention (tensor-core bound) ----

@@ -56,6 +56,7 @@ SIGNATURES = {
     "dinoseg_debug_heartbeat": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "dinoseg_profile_num_kinds": (C.c_int, []),
     "dinoseg_profile_kind_name": (C.c_char_p, [C.c_int]),
+    "dinoseg_profile_gaps": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "dinoseg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     "dinoseg_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -1089,6 +1089,23 @@ int dinoseg_debug_heartbeat(int* host_out, int n) {
 int dinoseg_profile_num_kinds(void) { return K_COUNT; }
 const char* dinoseg_profile_kind_name(int kind) { return (kind >= 0 && kind < K_COUNT) ? kKindNames[kind] : ""; }
 
+// Before dinoseg_profile_read: time between the first launch's start event and the last launch's end event, and the
+// part of it that lies BETWEEN launches (end event of one -> start event of the next; includes the event records).
+int dinoseg_profile_gaps(dinoseg_t* h, float* span_ms, float* gap_ms) {
+  if (!h || !span_ms || !gap_ms) return -1;
+  *span_ms = 0.f; *gap_ms = 0.f;
+  if (h->ev_used < 1) return 0;
+  cudaError_t e = cudaEventSynchronize(h->ev[2 * (h->ev_used - 1) + 1]);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(span_ms, h->ev[0], h->ev[2 * (h->ev_used - 1) + 1]);
+  for (int i = 0; e == cudaSuccess && i + 1 < h->ev_used; ++i) {
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, h->ev[2 * i + 1], h->ev[2 * (i + 1)]);
+    *gap_ms += ms;
+  }
+  if (e != cudaSuccess) DSG_FAIL(h, "dinoseg_profile_gaps: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds) {
   if (!h || !ms_by_kind || !launches_by_kind || n_kinds < K_COUNT) return -1;
   for (int k = 0; k < K_COUNT; ++k) { ms_by_kind[k] = 0.f; launches_by_kind[k] = 0; }

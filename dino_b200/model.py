@@ -562,6 +562,14 @@ class DINOSeg(nn.Module):
         self._check(lib.dinoseg_profile_read(self._handle, ms, cnt, n), "dinoseg_profile_read")
         return {lib.dinoseg_profile_kind_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
+    def profile_gaps(self):
+        """-> (span ms, gap ms) of the launches recorded since enable / the last read: first start -> last end, and the part
+        of it between launches.  Call BEFORE profile_read (which resets the record)."""
+        lib = self._ensure_handle()
+        span, gap = C.c_float(0.0), C.c_float(0.0)
+        self._check(lib.dinoseg_profile_gaps(self._handle, C.byref(span), C.byref(gap)), "dinoseg_profile_gaps")
+        return float(span.value), float(gap.value)
+
     def last_launch_count(self):
         return _lib.load().dinoseg_last_launch_count(self._handle) if self._handle is not None else 0
 

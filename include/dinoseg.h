@@ -179,6 +179,9 @@ int dinoseg_debug_heartbeat(int* host_out, int n);
 int dinoseg_profile_num_kinds(void);
 const char* dinoseg_profile_kind_name(int kind);
 int dinoseg_profile_read(dinoseg_t* h, float* ms_by_kind, int* launches_by_kind, int n_kinds);
+/* Call before dinoseg_profile_read: span_ms = first launch's start -> last launch's end, gap_ms = the part of it that
+ * lies between launches (measurement hook) */
+int dinoseg_profile_gaps(dinoseg_t* h, float* span_ms, float* gap_ms);
 
 /* ---- kernel-level entry points (parity tests of the individual CUDA kernels) ----------- */
 /* C[M,N] = A[M,K] bf16 x W[N,K]^T bf16 with epilogue `epi` (see csrc/gemm.cuh EPI_*) */
