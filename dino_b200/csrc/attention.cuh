@@ -371,6 +371,34 @@ __device__ __forceinline__ void att_exp_tile_chunked(uint32_t s_addr, uint32_t b
   att_exp_chunk<3, MASK>(cb, pk + 24, sum0, sum1, key0 + 96, N);
 }
 
+// The last key tile of a ragged sequence: only the 32-key chunks that hold existing keys are loaded and exponentiated
+// (3601 tokens: 17 keys = one chunk of four); the PV MMA of this tile reads only the K steps that cover them
+// (att_pv_ksteps), so the rest of P is never looked at.
+__device__ __forceinline__ void att_exp_tile_ragged(uint32_t s_addr, uint32_t b_s_empty, uint32_t (&pk)[32], float2& sum0,
+                                                    float2& sum1, int key0, int N, int nvc) {
+  uint32_t ca[16], cb[16];
+#pragma unroll
+  for (int i = 8; i < 32; ++i) pk[i] = 0u;
+  tmem_ld_16x256b_x4(s_addr, ca);
+  if (nvc > 1) tmem_ld_16x256b_x4(s_addr + 32, cb);
+  tmem_ld_wait();
+  att_exp_chunk<0, true>(ca, pk, sum0, sum1, key0, N);
+  if (nvc > 2) tmem_ld_16x256b_x4(s_addr + 64, ca);
+  if (nvc > 1) att_exp_chunk<1, true>(cb, pk + 8, sum0, sum1, key0 + 32, N);
+  if (nvc > 3) tmem_ld_16x256b_x4(s_addr + 96, cb);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive_a(b_s_empty);
+  if (nvc > 2) att_exp_chunk<2, true>(ca, pk + 16, sum0, sum1, key0 + 64, N);
+  if (nvc > 3) att_exp_chunk<3, true>(cb, pk + 24, sum0, sum1, key0 + 96, N);
+}
+
+// K = 16 steps of the PV MMA of key tile j: all eight, or, in the ragged last tile, those that cover existing keys
+__host__ __device__ __forceinline__ int att_pv_ksteps(int N, int j) {
+  const int left = N - j * ATT_BN;
+  return left >= ATT_BN ? ATT_BN / 16 : (left + 15) / 16;
+}
+
 __device__ __forceinline__ void att_softmax_unshifted(const AttnParams& p, const uint32_t tmem_base, const AttBars bars,
                                                       const int warp, const int lane, const int num_tiles) {
   const int t = (warp - 4) >> 3;
@@ -391,12 +419,28 @@ __device__ __forceinline__ void att_softmax_unshifted(const AttnParams& p, const
     const int q0 = t ? I.q0[1] : I.q0[0];
     float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);   // this thread's share of its two row sums
 
+    if (q0 + rbase >= p.N) {
+      // None of this warp's 16 query rows exists (last query tile of a ragged sequence: 17 of 128 rows at 3601 tokens).
+      // Nothing to compute - whatever the PV MMA makes of these rows of P is never stored - but the barriers count
+      // every thread of the query tile, phase by phase: s_empty after s_full (QK(j) is only issued once the previous
+      // s_empty phase is complete), p_full after PV(j-1) has retired (which implies the previous p_full phase is complete).
+      for (int j = 0; j < num_tiles; ++j, ++sc) {
+        mbar_wait_a(b_s_full, sc & 1);
+        mbar_arrive_a(b_s_empty);
+        if (j > 0) mbar_wait_a(b_pv_done, (sc - 1) & 1);
+        mbar_arrive_a(b_p_full);
+      }
+      mbar_wait_a(b_pv_done, (sc - 1) & 1);
+      continue;
+    }
+
     for (int j = 0; j < num_tiles; ++j, ++sc) {
       mbar_wait_a(b_s_full, sc & 1);
       tc_fence_after();
       uint32_t pk[32];
       const int kbase = j * ATT_BN;
-      if (kbase + ATT_BN > p.N) att_exp_tile_chunked<true>(s_addr, b_s_empty, pk, sum0, sum1, kbase + 2 * qd, p.N);
+      if (kbase + ATT_BN > p.N)
+        att_exp_tile_ragged(s_addr, b_s_empty, pk, sum0, sum1, kbase + 2 * qd, p.N, (p.N - kbase + 31) >> 5);
       else att_exp_tile_chunked<false>(s_addr, b_s_empty, pk, sum0, sum1, 0, 0);
       if (j > 0) {
         mbar_wait_a(b_pv_done, (sc - 1) & 1);      // PV_t(j-1) must have retired before P_t is overwritten
@@ -552,13 +596,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           umma_ss(s_tmem, qdesc + uint64_t(k * 2), kdesc + uint64_t(k * 2), idesc_qk, k != 0);
         tc_commit(&s_full[t]);
       };
-      auto issue_pv = [&](uint32_t kv_counter, bool accumulate) {
+      auto issue_pv = [&](uint32_t kv_counter, bool accumulate, int ksteps) {
         const uint32_t sv = smem_u32(sKV + size_t(kv_counter % KV_STAGES) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
         const uint64_t vdesc = umma_desc_sw128(sv);
         // P: 8 TMEM columns (16 bf16 keys) per K step; V: 16 keys = 2 KB per K step
+        // (the ragged last key tile: only the K steps that cover existing keys; the softmax warps of the kernel without
+        // row maxima do not produce the rest of P, the classic kernel writes zeros there)
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(o_tmem, p_tmem + uint32_t(k * 8), vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+          if (k < ksteps)
+            umma_ts(o_tmem, p_tmem + uint32_t(k * 8), vdesc + uint64_t(k * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
         tc_commit(&pv_done[t]);
       };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
@@ -600,7 +647,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
             mbar_wait(&p_full[t], ct & 1); ++ct;
             ATT_T(3);
             tc_fence_after();
-            issue_pv(own(j), j != 0);
+            issue_pv(own(j), j != 0, att_pv_ksteps(p.N, j));
             ATT_T(6);
           }
           tc_commit(&kv_empty[own(j) % KV_STAGES]);   // this tile's reads of K(j), V(j) have been issued
