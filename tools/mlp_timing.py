@@ -28,6 +28,10 @@ def main():
     have = lib.dinoseg_debug_set_attn_timing(timing.data_ptr()) == 0
     A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
     args = (x.data_ptr(), A.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, mc, None)
+    if os.environ.get("DSG_MLP_LN", "0") != "0":        # the kernel normalising x itself (LayerNorm2 fused)
+        lib.dinoseg_op_mlp_ln.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]
+        args = (x.data_ptr(), 1e-6, W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, mc, None)
+        lib.dinoseg_op_mlp_ex = lib.dinoseg_op_mlp_ln
     for _ in range(2):
         lib.dinoseg_op_mlp_ex(*args)
     torch.cuda.synchronize()
