@@ -386,8 +386,9 @@ def test_gpu_preprocessing_is_bit_exact(hw, res):
 @pytest.mark.parametrize("name", ["s8_nb1_240_refinit", "s8_nb3_240_b2_trained", "b8_nb4_240_refinit"])
 def test_cls_attention_against_reference(name):
     """model.dino.get_last_selfattention(x)[b, :, 0, :] (the row visualize_attention.py:46-54 reads) vs the reference's
-    (vision_transformer.py:273-280): rows are probability vectors; max error <= 2 % of the largest probability
-    (6 % for the peaked attention of the 'trained_like' stress weights, whose bf16 q/k rounding moves the logits by ~0.02)."""
+    (vision_transformer.py:273-280): rows are probability vectors; max error <= 1 % of the largest probability (measured
+    0.15 - 0.5 %; 6 % for the peaked attention of the 'trained_like' stress weights, whose bf16 q/k rounding moves the
+    logits by ~0.02: measured 5.2 %)."""
     gd, meta, m, cfg, sd, x = _case(name)
     att = m.dino.get_last_selfattention(x.cuda())
     torch.cuda.synchronize()
@@ -398,7 +399,7 @@ def test_cls_attention_against_reference(name):
     assert np.abs(got.sum(-1) - 1.0).max() <= 1e-5
     err = float(np.abs(got - ref).max())
     _record(case=name, cls_attn_max_abs=err, cls_attn_ref_max=float(ref.max()))
-    tol = 2e-2 if meta["variant"] == "reference_init" else 6e-2
+    tol = 1e-2 if meta["variant"] == "reference_init" else 6e-2
     assert err <= tol * float(ref.max()), (err, float(ref.max()))
 
 
