@@ -351,24 +351,24 @@ __device__ __forceinline__ void att_exp_chunk(uint32_t (&c)[16], uint32_t* pk, f
   }
 }
 
-template <bool MASK>
+// a full key tile: four chunks, each processed while the next one is in flight
 __device__ __forceinline__ void att_exp_tile_chunked(uint32_t s_addr, uint32_t b_s_empty, uint32_t (&pk)[32], float2& sum0,
-                                                     float2& sum1, int key0, int N) {
+                                                     float2& sum1) {
   uint32_t ca[16], cb[16];
   tmem_ld_16x256b_x4(s_addr, ca);
   tmem_ld_wait();
   tmem_ld_16x256b_x4(s_addr + 32, cb);
-  att_exp_chunk<0, MASK>(ca, pk, sum0, sum1, key0, N);
+  att_exp_chunk<0, false>(ca, pk, sum0, sum1, 0, 0);
   tmem_ld_wait();
   tmem_ld_16x256b_x4(s_addr + 64, ca);
-  att_exp_chunk<1, MASK>(cb, pk + 8, sum0, sum1, key0 + 32, N);
+  att_exp_chunk<1, false>(cb, pk + 8, sum0, sum1, 0, 0);
   tmem_ld_wait();
   tmem_ld_16x256b_x4(s_addr + 96, cb);
-  att_exp_chunk<2, MASK>(ca, pk + 16, sum0, sum1, key0 + 64, N);
+  att_exp_chunk<2, false>(ca, pk + 16, sum0, sum1, 0, 0);
   tmem_ld_wait();
   tc_fence_before();
   mbar_arrive_a(b_s_empty);                        // the tensor pipe may overwrite S_t with the next scores
-  att_exp_chunk<3, MASK>(cb, pk + 24, sum0, sum1, key0 + 96, N);
+  att_exp_chunk<3, false>(cb, pk + 24, sum0, sum1, 0, 0);
 }
 
 // The last key tile of a ragged sequence: only the 32-key chunks that hold existing keys are loaded and exponentiated
@@ -441,7 +441,7 @@ __device__ __forceinline__ void att_softmax_unshifted(const AttnParams& p, const
       const int kbase = j * ATT_BN;
       if (kbase + ATT_BN > p.N)
         att_exp_tile_ragged(s_addr, b_s_empty, pk, sum0, sum1, kbase + 2 * qd, p.N, (p.N - kbase + 31) >> 5);
-      else att_exp_tile_chunked<false>(s_addr, b_s_empty, pk, sum0, sum1, 0, 0);
+      else att_exp_tile_chunked(s_addr, b_s_empty, pk, sum0, sum1);
       if (j > 0) {
         mbar_wait_a(b_pv_done, (sc - 1) & 1);      // PV_t(j-1) must have retired before P_t is overwritten
         tc_fence_after();
